@@ -1,0 +1,263 @@
+"""bench.py — image-pairs/s of the RAFT-NCUP hot path at 1024x436, 32 iterations (BASELINE.json metric), with the
+corr-lookup kernel's HBM roofline and the CPU baseline beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" = one RAFT.forward over one batch of synthetic pairs (BASELINE configs[2]: batch 8 per GPU, 1024x436 padded to
+440, 32 iterations, model raft_nc_dbl = full path incl. the NCUP upsampler; configs[1]'s corr-lookup kernel is timed
+inside the same steps).  Weak scaling: every rank runs an independent replica on its own 8 pairs, no data-path collective.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "raft-ncup_b200"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+H_IMG, W_IMG, ITERS, BATCH = 436, 1024, 32, 8
+K2_BYTES_PER_PAIR_ITER = 25_891_840      # fmap1 + coords + out + fmap2 pyramid, fp32
+K4_BYTES_PER_PAIR_CALL = 3_886_080       # flow_lr + conf read, 2x64xP fp32 written
+METRIC = "image-pairs/sec @ 1024x436, 32 iters"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def synth_frames(b, seed):
+    g = torch.Generator().manual_seed(seed)
+    im1 = torch.rand(b, 3, H_IMG, W_IMG, generator=g) * 255
+    im2 = torch.rand(b, 3, H_IMG, W_IMG, generator=g) * 255
+    from utils.utils import InputPadder
+    return InputPadder(im1.shape, "sintel").pad(im1, im2)           # 436 -> 440 (evaluate.py:125-126)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.proc.wait()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_oracle_pairs_per_s(steps, warmup):
+    """The reference's algorithm on the host cores: oracle/raft_oracle.py (a torch-CPU restatement pinned to the reference
+    by tests/golden).  One step = ONE pair at the full 1024x436 / 32-iteration shape (bounded sample of the 8-pair batch)."""
+    from conftest import build_model
+    from oracle import raft_oracle as orc
+    torch.set_num_threads(os.cpu_count())
+    sd = {k: v.detach() for k, v in build_model("raft_nc_dbl").state_dict().items()}
+    p1, p2 = synth_frames(1, 7)
+    for _ in range(warmup):
+        orc.raft_forward(sd, p1, p2, iters=ITERS, model="raft_nc_dbl")
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.raft_forward(sd, p1, p2, iters=ITERS, model="raft_nc_dbl")      # upsamples every iteration, like raft_nc_dbl.py:161
+    dt = (time.perf_counter() - t0) / steps
+    return 1.0 / dt, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps, warmup = args.steps, args.warmup
+    v, dt = cpu_oracle_pairs_per_s(steps, min(warmup, 1))
+    cores = torch.get_num_threads()
+    sample = "1 pair per step at 1024x436 (pad 440), 32 iters, NCUP upsampling every iteration as the reference does"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2/3: 1024x436 (pad 440), 32 iters, raft_nc_dbl full path incl. NCUP", "device": "host CPU"},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def mean_ms(pairs):
+    return sum(a.elapsed_time(b) for a, b in pairs) / max(len(pairs), 1)
+
+
+def run_native(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from conftest import build_model
+    from rnc import native
+    assert torch.cuda.is_available(), "bench.py --impl native needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    model = build_model(args.model).to(dev)
+    p1, p2 = synth_frames(args.batch, 7 + rank)
+    h1, h2 = p1.pin_memory(), p2.pin_memory()                      # host buffers of the e2e arm
+    d1, d2 = h1.to(dev), h2.to(dev)                                # resident inputs of the `value` arm
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    out_lo = torch.empty(args.batch, 2, 55, 128).pin_memory()
+    out_up = torch.empty(args.batch, 2, 440, 1024).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        with torch.no_grad():
+            return model(d1, d2, iters=ITERS, test_mode=True)
+
+    def step_e2e():
+        with torch.no_grad():
+            a, b = h1.to(dev, non_blocking=True), h2.to(dev, non_blocking=True)
+            lo, up = model(a, b, iters=ITERS, test_mode=True)
+            out_lo.copy_(lo, non_blocking=True)
+            out_up.copy_(up, non_blocking=True)
+        return lo, up
+
+    def timed(fn, steps):
+        evs = []
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            flush.zero_()                                           # L2 flush between timed iterations (not timed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        wall = time.perf_counter() - t0
+        dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)                # max over ranks
+        return t.item(), wall
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    step_e2e()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    eng = model.engine()
+    eng.profile = {}
+    native.launch_count_reset()
+    ms_total, wall = timed(step_resident, args.steps)
+    launches = native.launch_count()
+    prof, eng.profile = eng.profile, None
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    pairs = world * args.batch * args.steps
+    value = pairs / (ms_total * 1e-3)
+    e2e = pairs / (ms_e2e * 1e-3)
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    k2_ms = mean_ms(prof.get("corr_lookup", []))
+    k2_bytes = K2_BYTES_PER_PAIR_ITER * args.batch
+    k2_gbs = k2_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms else 0.0
+    k4_ms = mean_ms(prof.get("ncup", []))
+    k4_gbs = K4_BYTES_PER_PAIR_CALL * args.batch / (k4_ms * 1e-3) / 1e9 if k4_ms else 0.0
+    ub_ms = mean_ms(prof.get("update_block", []))
+    ub_tflops = 37.7e9 * args.batch / (ub_ms * 1e-3) / 1e12 if ub_ms else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cfg2/3: batch={args.batch}/GPU 1024x436 (pad 440), 32 iters, {args.model} full path "
+                               "(encoders + corr lookup + update block + NCUP upsampler), random-init weights seed 1234",
+                   "parallelism": f"replicas x{world} (batch-sharded, no collective)",
+                   "l2": "flushed with a 256 MiB write between timed steps", "timing": "CUDA events per step, max over ranks",
+                   "wall_s_incl_flush": wall},
+        "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(h1.numel() + h2.numel()) * 4,
+                "d2h_bytes_per_step": int(out_lo.numel() + out_up.numel()) * 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "corr_lookup_tile_kernel (fused corr lookup, K2)", "bound": "hbm", "achieved": k2_gbs, "peak": peak,
+                     "unit": "GB/s", "frac": k2_gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": k2_bytes, "avg_launch_ms": k2_ms,
+                     "launches_timed": len(prof.get("corr_lookup", []))},
+        "roofline_ncup": {"kernel": "ncup_fused_kernel (K4)", "bound": "hbm", "achieved": k4_gbs, "peak": peak, "unit": "GB/s",
+                          "frac": k4_gbs / peak, "avg_launch_ms": k4_ms,
+                          "algorithmic_bytes_per_launch": K4_BYTES_PER_PAIR_CALL * args.batch},
+        "update_block": {"avg_iter_ms": ub_ms, "tflops_fp32_equiv": ub_tflops, "flop_per_pair_iter": 37.7e9},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt = cpu_oracle_pairs_per_s(1, 0)
+        line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "1 pair (of the 8-pair batch) at 1024x436/32 iters through oracle/raft_oracle.py, "
+                                          f"1 run, {dt:.1f} s"}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--model", default="raft_nc_dbl", choices=["raft_nc_dbl", "raft"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="pairs per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_native(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,168 @@
+/* rnc.h — C ABI of librnc.so: the B200 (sm_100a) kernels behind RAFT-NCUP's per-iteration hot path.
+ *
+ * The reference (abdo-eldesokey/RAFT-NCUP @ 51ac387) has NO native layer: every op below is a chain of
+ * PyTorch eager calls.  Each entry point therefore cites the reference *Python* interface it replaces
+ * (file:line under /root/reference).  INTEGRATION.md shows the ctypes stub a maintainer of the reference
+ * would add at each call site.
+ *
+ * Conventions
+ *   - every function returns 0 (RNC_OK) or a negative rnc_status; nothing throws across the boundary
+ *   - all pointers are DEVICE pointers to caller-owned buffers (e.g. torch tensor.data_ptr()); no hidden
+ *     allocation, no global mutable state, re-entrant; work is enqueued on `stream` (a cudaStream_t passed
+ *     as void*) and the call returns immediately
+ *   - "NCHW" tensors are the reference's own layout; "CL" = channel-last [B][H][W][C] fp32, the resident
+ *     layout of the 1/8-resolution activations inside the iteration loop
+ */
+#ifndef RNC_H_
+#define RNC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  RNC_OK = 0,
+  RNC_ERR_BAD_SHAPE = -1,     /* dimension <= 0, unsupported radius/levels/channel count */
+  RNC_ERR_BAD_POINTER = -2,   /* null or misaligned (16 B) pointer */
+  RNC_ERR_UNSUPPORTED = -3,   /* valid request this build does not implement */
+  RNC_ERR_CUDA = -4,          /* launch failed; see rnc_last_cuda_error() */
+  RNC_ERR_WORKSPACE = -5      /* workspace too small */
+} rnc_status;
+
+/* Library identity / diagnostics. */
+int rnc_abi_version(void);                 /* bumps on any signature change */
+const char* rnc_build_info(void);          /* e.g. "sm_100a nvcc 12.9" */
+const char* rnc_status_string(int status);
+int rnc_last_cuda_error(void);             /* cudaError_t of the last failed launch on this thread */
+/* Number of kernels launched by this library on the calling thread since the last reset (bench.py's
+ * `gpu_launches` claim is read from here). */
+long long rnc_launch_count(void);
+void rnc_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * A1  CorrBlock.__init__  (core/corr.py:7-21, 47-55)
+ * Replaces the all-pairs matmul + avg_pool2d pyramid.  Nothing quadratic is built: fmap1 is transposed to
+ * CL and fmap2 is transposed + average-pooled (floor mode, 2x2) into a `levels`-deep CL pyramid; pooling
+ * commutes with the dot product so lookups against it equal lookups into the reference's 4-D pyramid.
+ *   fmap1, fmap2 : [B][D][H][W] fp32 NCHW
+ *   f1_cl        : [B][H*W][D]
+ *   f2_pyr       : level l at element offset rnc_pyramid_offset(B,D,H,W,l), shape [B][H>>l][W>>l][D]
+ */
+size_t rnc_pyramid_offset(int B, int D, int H, int W, int level);   /* in elements; level==levels -> total */
+int rnc_fmap_prepare(const float* fmap1, const float* fmap2, int B, int D, int H, int W, int levels,
+                     float* f1_cl, float* f2_pyr, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A2/A3  CorrBlock.__call__ + bilinear_sampler  (core/corr.py:23-44, core/utils/utils.py:59-73)
+ * Fused multi-scale lookup straight from the feature maps.
+ *   coords : [B][2][H][W] fp32 NCHW (channel 0 = x, 1 = y), level-0 pixel units
+ *   out    : layout 0 -> [B][L*(2r+1)^2][H][W]   (the reference's return value, corr.py:44)
+ *            layout 1 -> CL [B][H][W][ldo], channels [0, L*(2r+1)^2) written, ldo >= that
+ *   channel k = l*(2r+1)^2 + i*(2r+1) + j  samples level l at (cx/2^l + i - r, cy/2^l + j - r): the slow
+ *   window index offsets x (corr.py:31-37).  Bilinear, zero outside, scaled by 1/sqrt(D).
+ * Supported: D % 32 == 0, radius == 4 (the only value the reference's models use, raft_nc_dbl.py:41), 1 <= levels <= 4.
+ */
+int rnc_corr_lookup_fwd(const float* f1_cl, const float* f2_pyr, const float* coords,
+                        int B, int D, int H, int W, int levels, int radius,
+                        float* out, int layout, int ldo, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A5..A8  update block convolutions  (core/update.py:6-14, 33-60, 79-97, 114-141)
+ * One generic channel-last convolution with the update block's fusions expressed as epilogues.
+ * The input is the virtual concatenation of up to two CL segments (replaces torch.cat, update.py:46,49,95,132).
+ * weight is pre-packed [KH*KW][Cin][CoutPad] fp32 (CoutPad = Cout rounded up to 64), bias [CoutPad].
+ */
+typedef enum {
+  RNC_EPI_LINEAR = 0,   /* out = acc + bias                                                     */
+  RNC_EPI_RELU = 1,     /* out = relu(acc + bias)                       update.py:90-96, 14     */
+  RNC_EPI_SIGMOID = 2,  /* out = sigmoid(acc + bias)                                            */
+  RNC_EPI_GRU_ZR = 3,   /* Cout = 2*C: ch<C: aux0[p][ch] = z = sigmoid(.)                       */
+                        /*             ch>=C: out[p][ch-C] = sigmoid(.) * h[p][ch-C]   update.py:47-49 */
+  RNC_EPI_GRU_Q = 4,    /* q = tanh(.); h[p][ch] = (1-z)*h + z*q with z = aux0       update.py:49-50 */
+  RNC_EPI_RELU_FLOW = 5 /* RELU, and channels [Cout, Cout+2) of out receive flow = coords1-coords0 (update.py:97);
+                           aux0 = coords1 NCHW [B][2][H][W]                                     */
+} rnc_epilogue;
+
+typedef struct {
+  const float* in0; int c0; int ld0;   /* segment 0: channels [0,c0), pixel stride ld0 floats   */
+  const float* in1; int c1; int ld1;   /* segment 1 (optional, c1 = 0 if absent)                */
+  const float* weight; const float* bias;
+  float* out; int ldo;                 /* CL output, pixel stride ldo                           */
+  float* h; int ldh;                   /* GRU hidden state (read; written by GRU_Q)             */
+  float* aux0; int ldaux;              /* z buffer (GRU) or coords1 (RELU_FLOW)                 */
+  int B, H, W;
+  int cout;                            /* logical Cout (<= CoutPad)                             */
+  int kh, kw;                          /* odd; zero padding kh/2, kw/2 (all reference convs)    */
+  int epilogue;                        /* rnc_epilogue                                          */
+} rnc_conv_desc;
+
+int rnc_conv2d_cl_fwd(const rnc_conv_desc* desc, void* stream);
+
+/* convf1: Conv2d(2,128,7,padding=3)+ReLU on flow = coords1 - coords0 (update.py:83,92).
+ * coords1 NCHW [B][2][H][W]; weight packed [49][2][Cout]; out CL. */
+int rnc_conv_flow7x7_fwd(const float* coords1, const float* weight, const float* bias, int B, int H, int W,
+                         int cout, float* out, int ldo, void* stream);
+
+/* FlowHead.conv2 (update.py:10,14) fused with `coords1 = coords1 + delta_flow` (raft_nc_dbl.py:157):
+ * in CL [B][H][W][cin]; weight packed [9][cin][2]; delta (optional, may be NULL) and coords1 NCHW [B][2][H][W]. */
+int rnc_flow_head2_fwd(const float* in, int cin, int ldi, const float* weight, const float* bias,
+                       int B, int H, int W, float* delta, float* coords1, void* stream);
+
+/* coords_grid / initialize_flow (core/utils/utils.py:76-79, raft_nc_dbl.py:83-90) (+ optional flow_init, :144-145).
+ * coords1 = grid (+ flow_init);  flow_init may be NULL. */
+int rnc_coords_init(float* coords1, const float* flow_init, int B, int H, int W, void* stream);
+/* flow = coords1 - grid  -> NCHW [B][2][H][W]  (raft_nc_dbl.py:152,170). */
+int rnc_coords_to_flow(const float* coords1, float* flow, int B, int H, int W, void* stream);
+
+/* Layout plumbing between the reference's NCHW tensors and the resident CL buffers. */
+int rnc_nchw_to_cl(const float* src, int B, int C, int H, int W, float* dst, int ldd, int ch_off, void* stream);
+int rnc_cl_to_nchw(const float* src, int lds, int ch_off, int B, int C, int H, int W, float* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * U1  RAFT.upsample_flow, convex combination  (core/raft.py:73-84)
+ *   flow NCHW [B][2][H8][W8]; mask CL [B][H8][W8][ldm] with 576 logits (c = k*64 + sy*8 + sx, k = ky*3+kx),
+ *   already scaled by 0.25 (update.py:140); out NCHW [B][2][8*H8][8*W8].
+ */
+int rnc_convex_upsample_fwd(const float* flow, const float* mask, int ldm, int B, int H8, int W8,
+                            float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * U2  RAFT.upsample_flow prologue (raft_nc_dbl.py:110): x4 = nearest-x2 of flow_lr = coords1 - grid.
+ *   coords1 NCHW [B][2][H8][W8] -> x4 NCHW [B][2][2*H8][2*W8]
+ */
+int rnc_flow_x2_fwd(const float* coords1, int B, int H8, int W8, float* x4, void* stream);
+
+/* U3 (input staging)  upsampler.py:150,155 — builds the weights-net input at 1/4 resolution, CL [B][2*H8][2*W8][ldo]:
+ *   channels 0,1 = x_lowres (NCHW [B][2][2*H8][2*W8]); channels 2..2+C = guidance (net, CL [B][H8][W8][ldg]) resized
+ *   'area' H8 -> 2*H8, which for an integer x2 upscale is replication; channels >= 2+C are zero-filled.
+ */
+int rnc_ncup_guidance_fwd(const float* x_lowres, const float* net, int ldg, int C, int B, int H8, int W8,
+                          float* out, int ldo, void* stream);
+
+/* U4 tail: Simple.out (1x1 conv 32->2) + sigmoid (interp_weights_est.py:37,47; upsampler.py:44-46):
+ *   in CL [B][H4][W4][cin] -> conf NCHW [B][2][H4][W4]. weight packed [cin][2]. */
+int rnc_conf_head_fwd(const float* in, int cin, int ldi, const float* weight, const float* bias,
+                      int B, int H4, int W4, float* conf, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * U3/U5/U6  NConvUpsampler.forward + NConvUNet.forward (live path) + NConv2d.forward
+ *           (core/upsampler.py:143-177,179-210; core/nconv_modules.py:106-136,164-199)
+ * Fused zero-stuff (scale 4, offset 2) + 4 normalized convolutions + the x8 of raft_nc_dbl.py:161.
+ *   x_lowres: NCHW [B][2][H4][W4]   low-resolution data (in RAFT: nearest-x2 flow at 1/4 resolution)
+ *   conf    : NCHW [B][2][H4][W4]   sigmoid output of the weights net
+ *   wts_host: HOST pointer to 224 floats = softplus_{beta=10}(weight_p) of nconv_in[2,1,5,5], nconv_x2.0[2,2,5,5],
+ *             decoder.0[2,4,3,3], nconv_out[1,2,1,1] in that order (nconv_modules.py:250-264).  They are copied
+ *             into the kernel's parameter bank at launch (read before the call returns), so the call stays
+ *             re-entrant with no device-side global state.
+ *   out     : NCHW [B][2][4*H4][4*W4] = out_scale * NConvUNet output  (out_scale = 8 in RAFT, raft_nc_dbl.py:161)
+ */
+int rnc_ncup_fwd(const float* x_lowres, const float* conf, const float* wts_host, int B, int H4, int W4,
+                 float out_scale, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNC_H_ */

@@ -1,0 +1,47 @@
+// Shared helpers for the rnc kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "rnc.h"
+
+namespace rnc {
+
+extern thread_local int g_last_cuda_error;
+extern thread_local long long g_launch_count;
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+__device__ __forceinline__ bool aligned16_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+#define RNC_XSTR(x) #x
+#define RNC_STR(x) RNC_XSTR(x)
+#define RNC_STR_CUDA RNC_STR(__CUDACC_VER_MAJOR__) "." RNC_STR(__CUDACC_VER_MINOR__)
+
+// Opt a kernel into > 48 KB of dynamic shared memory, once per device.
+template <typename K>
+inline int ensure_dyn_smem(K kernel, int bytes, unsigned long long* done_mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (__atomic_load_n(done_mask, __ATOMIC_ACQUIRE) & bit) return RNC_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) { g_last_cuda_error = static_cast<int>(e); return RNC_ERR_CUDA; }
+  __atomic_fetch_or(done_mask, bit, __ATOMIC_RELEASE);
+  return RNC_OK;
+}
+
+// Record a launch and translate the launch status.
+inline int after_launch(int n = 1) {
+  g_launch_count += n;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    g_last_cuda_error = static_cast<int>(e);
+    return RNC_ERR_CUDA;
+  }
+  return RNC_OK;
+}
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+}  // namespace rnc

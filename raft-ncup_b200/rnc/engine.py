@@ -1,0 +1,301 @@
+"""Host-side driver of the per-iteration hot path: owns the resident channel-last (CL) workspace and issues the
+librnc kernels in the order of the reference's loop body.
+
+Reference control flow being replaced (file:line under /root/reference/core):
+  raft_nc_dbl.py:148-165 / raft.py:121-138   for itr in range(iters): lookup -> update block -> coords += delta -> upsample
+  update.py:130-141                          BasicUpdateBlock.forward
+  raft_nc_dbl.py:107-112, upsampler.py:143-177   NCUP upsampling          raft.py:73-84  convex upsampling
+
+PyTorch is used here only as plumbing: device memory (torch.empty), the current CUDA stream and weight
+re-packing at load time.  All arithmetic of the path runs in librnc.so; there is no fallback.
+"""
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+
+from . import native
+from .native import ConvDesc
+
+CORR_CH = 324          # 4 levels * 9 * 9
+HX_LD = 384            # [h | inp | motion(126) flow(2)]
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise native.RncUnavailable(
+                "the RAFT-NCUP hot path runs only on CUDA (sm_100a) tensors; got a CPU tensor and there is no CPU fallback")
+
+
+def pack_conv(weight, bias, cin_pad=None, scale=1.0):
+    """[Cout,Cin,KH,KW] -> ([KH*KW][CinPad][CoutPad], [CoutPad]) fp32, CoutPad = ceil64(Cout)."""
+    cout, cin, kh, kw = weight.shape
+    cin_pad = cin_pad or cin
+    cout_pad = (cout + 63) // 64 * 64
+    w = torch.zeros(kh * kw, cin_pad, cout_pad, dtype=torch.float32, device=weight.device)
+    w[:, :cin, :cout] = (weight.detach().float() * scale).permute(2, 3, 1, 0).reshape(kh * kw, cin, cout)
+    b = torch.zeros(cout_pad, dtype=torch.float32, device=weight.device)
+    if bias is not None:
+        b[:cout] = bias.detach().float() * scale
+    return w.contiguous(), b
+
+
+def pack_thin(weight):
+    """[Cout,Cin,KH,KW] -> [KH*KW][Cin][Cout] (no padding) for the thin-channel kernels."""
+    cout, cin, kh, kw = weight.shape
+    return weight.detach().float().permute(2, 3, 1, 0).reshape(kh * kw, cin, cout).contiguous()
+
+
+class PackedUpdateBlock:
+    """Kernel-ready weights of BasicUpdateBlock (update.py:114-128)."""
+
+    def __init__(self, ub):
+        e, g, fh = ub.encoder, ub.gru, ub.flow_head
+        self.convc1 = pack_conv(e.convc1.weight, e.convc1.bias)
+        self.convc2 = pack_conv(e.convc2.weight, e.convc2.bias)
+        self.convf1 = (pack_thin(e.convf1.weight), e.convf1.bias.detach().float().contiguous())
+        self.convf2 = pack_conv(e.convf2.weight, e.convf2.bias)
+        self.conv = pack_conv(e.conv.weight, e.conv.bias)
+        self.zr1 = pack_conv(torch.cat([g.convz1.weight, g.convr1.weight], 0), torch.cat([g.convz1.bias, g.convr1.bias], 0))
+        self.q1 = pack_conv(g.convq1.weight, g.convq1.bias)
+        self.zr2 = pack_conv(torch.cat([g.convz2.weight, g.convr2.weight], 0), torch.cat([g.convz2.bias, g.convr2.bias], 0))
+        self.q2 = pack_conv(g.convq2.weight, g.convq2.bias)
+        self.fh1 = pack_conv(fh.conv1.weight, fh.conv1.bias)
+        self.fh2 = (pack_thin(fh.conv2.weight), fh.conv2.bias.detach().float().contiguous())
+        self.has_mask = len(ub.mask) > 0
+        if self.has_mask:
+            self.m0 = pack_conv(ub.mask[0].weight, ub.mask[0].bias)
+            self.m2 = pack_conv(ub.mask[2].weight, ub.mask[2].bias, scale=0.25)   # `.25 * self.mask(net)`, update.py:140
+
+
+class PackedUpsampler:
+    """Kernel-ready weights of NConvUpsampler (upsampler.py:75-141): BN-folded weights net + softplus'd NConv weights."""
+
+    def __init__(self, up):
+        wn = up.weights_est_net
+        convs = []
+        for blk in wn.conv:
+            conv = blk[0]
+            w, b = conv.weight.detach().float(), conv.bias.detach().float()
+            if len(blk) == 3:   # Conv, BatchNorm, ReLU — eval-mode fold (interp_weights_est.py:26-30)
+                bn = blk[1]
+                s = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+                w = w * s.view(-1, 1, 1, 1)
+                b = (b - bn.running_mean) * s + bn.bias.detach()
+            convs.append((w, b))
+        cin0 = convs[0][0].shape[1]
+        self.cin0_pad = (cin0 + 3) // 4 * 4
+        self.g0 = pack_conv(convs[0][0], convs[0][1], cin_pad=self.cin0_pad)
+        self.g1 = pack_conv(convs[1][0], convs[1][1])
+        self.c_mid0, self.c_mid1 = convs[0][0].shape[0], convs[1][0].shape[0]
+        self.gout = (pack_thin(wn.out.weight), wn.out.bias.detach().float().contiguous())
+        net = up.interpolation_net
+        ws = [F.softplus(p.detach().float(), beta=10).reshape(-1).cpu() for p in
+              (net.nconv_in.weight_p, net.nconv_x2[0].weight_p, net.decoder[0].weight_p, net.nconv_out.weight_p)]
+        host = torch.cat(ws).contiguous()
+        assert host.numel() == 224, "NCUP kernel is built for the shipped interp_net config (SURVEY.md §5)"
+        self.nconv_host = (C.c_float * 224)(*host.tolist())
+
+
+def _param_key(module):
+    return tuple((p.data_ptr(), p._version) for p in list(module.parameters()) + list(module.buffers()))
+
+
+class Workspace:
+    """Resident buffers for one (device, B, H8, W8).  Sized once; reused by every forward."""
+
+    def __init__(self, device, B, H8, W8, with_mask, with_ncup):
+        self.key = (str(device), B, H8, W8, with_mask, with_ncup)
+        self.B, self.H8, self.W8 = B, H8, W8
+        M = B * H8 * W8
+        f = dict(dtype=torch.float32, device=device)
+        self.hx = torch.zeros(M, HX_LD, **f)
+        self.corr = torch.empty(M, CORR_CH, **f)
+        self.c1 = torch.empty(M, 256, **f)
+        self.corflo = torch.empty(M, 256, **f)
+        self.f1 = torch.empty(M, 128, **f)
+        self.z = torch.empty(M, 128, **f)
+        self.rh = torch.empty(M, 128, **f)
+        self.fh = torch.empty(M, 256, **f)
+        self.coords1 = torch.empty(B, 2, H8, W8, **f)
+        self.delta = torch.empty(B, 2, H8, W8, **f)
+        self.f1_cl = None
+        self.f2_pyr = None
+        if with_mask:
+            self.mh = torch.empty(M, 256, **f)
+            self.mask = torch.empty(M, 576, **f)
+        if with_ncup:
+            M4 = 4 * M
+            self.x4 = torch.empty(B, 2, 2 * H8, 2 * W8, **f)
+            self.gin = torch.empty(M4, 132, **f)
+            self.g1 = torch.empty(M4, 64, **f)
+            self.g2 = torch.empty(M4, 32, **f)
+            self.conf = torch.empty(B, 2, 2 * H8, 2 * W8, **f)
+
+
+class _Timed:
+    """CUDA-event bracket on the launching stream, active only while Engine.profile is a dict (bench.py)."""
+
+    def __init__(self, eng, name):
+        self.eng, self.name = eng, name
+
+    def __enter__(self):
+        if self.eng.profile is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if self.eng.profile is not None:
+            self.e1.record()
+            self.eng.profile.setdefault(self.name, []).append((self.e0, self.e1))
+        return False
+
+
+class Engine:
+    """Issues the kernels.  One per model instance; keeps packed weights and workspaces."""
+
+    def __init__(self):
+        self.profile = None
+        self._packed_ub = None
+        self._packed_up = None
+        self._ub_key = None
+        self._up_key = None
+        self._ws = {}
+        self.L = native.lib()
+
+    # ------------------------------------------------------------------ caches
+    def packed_update(self, ub):
+        key = _param_key(ub)
+        if key != self._ub_key:
+            self._packed_ub, self._ub_key = PackedUpdateBlock(ub), key
+        return self._packed_ub
+
+    def packed_upsampler(self, up):
+        key = _param_key(up)
+        if key != self._up_key:
+            self._packed_up, self._up_key = PackedUpsampler(up), key
+        return self._packed_up
+
+    def workspace(self, device, B, H8, W8, with_mask, with_ncup):
+        key = (str(device), B, H8, W8, with_mask, with_ncup)
+        ws = self._ws.get(key)
+        if ws is None:
+            if len(self._ws) >= 4:
+                self._ws.clear()
+            ws = self._ws[key] = Workspace(device, B, H8, W8, with_mask, with_ncup)
+        return ws
+
+    # ------------------------------------------------------------------ single kernels
+    def conv(self, B, H, W, in0, c0, ld0, packed, cout, kh, kw, epi, out=None, ldo=0, in1=None, c1=0, ld1=0,
+             h=None, ldh=0, aux0=None, ldaux=0):
+        d = ConvDesc()
+        d.in0, d.c0, d.ld0 = in0, c0, ld0
+        d.in1, d.c1, d.ld1 = (in1 or 0), c1, ld1
+        d.weight, d.bias = packed[0].data_ptr(), packed[1].data_ptr()
+        d.out, d.ldo = (out or 0), ldo
+        d.h, d.ldh = (h or 0), ldh
+        d.aux0, d.ldaux = (aux0 or 0), ldaux
+        d.B, d.H, d.W = B, H, W
+        d.cout, d.kh, d.kw, d.epilogue = cout, kh, kw, epi
+        native.check(self.L.rnc_conv2d_cl_fwd(C.byref(d), _stream()), "conv2d_cl")
+
+    def fmap_prepare(self, ws, fmap1, fmap2, levels=4):
+        B, D, H, W = fmap1.shape
+        total = self.L.rnc_pyramid_offset(B, D, H, W, levels)
+        if ws.f1_cl is None or ws.f1_cl.numel() != B * H * W * D:
+            ws.f1_cl = torch.empty(B * H * W, D, dtype=torch.float32, device=fmap1.device)
+            ws.f2_pyr = torch.empty(total, dtype=torch.float32, device=fmap1.device)
+        native.check(self.L.rnc_fmap_prepare(_ptr(fmap1), _ptr(fmap2), B, D, H, W, levels, _ptr(ws.f1_cl),
+                                             _ptr(ws.f2_pyr), _stream()), "fmap_prepare")
+        ws.D, ws.levels = D, levels
+
+    def lookup(self, ws, coords, out, layout, ldo, radius=4):
+        with _Timed(self, "corr_lookup"):
+            native.check(self.L.rnc_corr_lookup_fwd(_ptr(ws.f1_cl), _ptr(ws.f2_pyr), _ptr(coords), ws.B, ws.D, ws.H8, ws.W8,
+                                                    ws.levels, radius, _ptr(out), layout, ldo, _stream()), "corr_lookup")
+
+    # ------------------------------------------------------------------ update block on resident buffers
+    def update_iter(self, ws, pk, want_mask=False, want_delta=False):
+        """update.py:130-141 on the CL workspace: consumes ws.corr and ws.coords1, advances ws.hx[:, :128] (net) and
+        ws.coords1 (raft_nc_dbl.py:157).  Optionally leaves the mask logits in ws.mask and delta in ws.delta."""
+        with _Timed(self, "update_block"):
+            self._update_iter(ws, pk, want_mask, want_delta)
+
+    def _update_iter(self, ws, pk, want_mask, want_delta):
+        B, H, W = ws.B, ws.H8, ws.W8
+        s = _stream()
+        hx = ws.hx.data_ptr()
+        x_ptr = hx + 128 * 4          # channels 128.. = [inp | motion | flow]
+        mot_ptr = hx + 256 * 4
+        # BasicMotionEncoder (update.py:89-97)
+        self.conv(B, H, W, ws.corr.data_ptr(), CORR_CH, CORR_CH, pk.convc1, 256, 1, 1, native.EPI_RELU, ws.c1.data_ptr(), 256)
+        self.conv(B, H, W, ws.c1.data_ptr(), 256, 256, pk.convc2, 192, 3, 3, native.EPI_RELU, ws.corflo.data_ptr(), 256)
+        native.check(self.L.rnc_conv_flow7x7_fwd(_ptr(ws.coords1), _ptr(pk.convf1[0]), _ptr(pk.convf1[1]), B, H, W, 128,
+                                                 _ptr(ws.f1), 128, s), "convf1")
+        self.conv(B, H, W, ws.f1.data_ptr(), 128, 128, pk.convf2, 64, 3, 3, native.EPI_RELU, ws.corflo.data_ptr() + 192 * 4, 256)
+        self.conv(B, H, W, ws.corflo.data_ptr(), 256, 256, pk.conv, 126, 3, 3, native.EPI_RELU_FLOW, mot_ptr, HX_LD,
+                  aux0=ws.coords1.data_ptr(), ldaux=0)
+        # SepConvGRU (update.py:45-60): horizontal (1x5) then vertical (5x1) half steps
+        for zr, q, kh, kw in ((pk.zr1, pk.q1, 1, 5), (pk.zr2, pk.q2, 5, 1)):
+            self.conv(B, H, W, hx, HX_LD, HX_LD, zr, 256, kh, kw, native.EPI_GRU_ZR, ws.rh.data_ptr(), 128,
+                      h=hx, ldh=HX_LD, aux0=ws.z.data_ptr(), ldaux=128)
+            self.conv(B, H, W, ws.rh.data_ptr(), 128, 128, q, 128, kh, kw, native.EPI_GRU_Q, in1=x_ptr, c1=256, ld1=HX_LD,
+                      h=hx, ldh=HX_LD, aux0=ws.z.data_ptr(), ldaux=128)
+        # FlowHead (update.py:13-14) + coords1 += delta (raft_nc_dbl.py:157)
+        self.conv(B, H, W, hx, 128, HX_LD, pk.fh1, 256, 3, 3, native.EPI_RELU, ws.fh.data_ptr(), 256)
+        native.check(self.L.rnc_flow_head2_fwd(_ptr(ws.fh), 256, 256, _ptr(pk.fh2[0]), _ptr(pk.fh2[1]), B, H, W,
+                                               _ptr(ws.delta) if want_delta else C.c_void_p(0), _ptr(ws.coords1), s), "flow_head2")
+        if want_mask:
+            # mask head (update.py:123-126,140), 0.25 folded into the 1x1 weights
+            self.conv(B, H, W, hx, 128, HX_LD, pk.m0, 256, 3, 3, native.EPI_RELU, ws.mh.data_ptr(), 256)
+            self.conv(B, H, W, ws.mh.data_ptr(), 256, 256, pk.m2, 576, 1, 1, native.EPI_LINEAR, ws.mask.data_ptr(), 576)
+
+    def load_state(self, ws, net, inp):
+        """NCHW net/inp (raft_nc_dbl.py:137-140) -> resident hx buffer."""
+        B, _, H, W = net.shape
+        s = _stream()
+        native.check(self.L.rnc_nchw_to_cl(_ptr(net), B, 128, H, W, _ptr(ws.hx), HX_LD, 0, s), "nchw_to_cl(net)")
+        native.check(self.L.rnc_nchw_to_cl(_ptr(inp), B, 128, H, W, _ptr(ws.hx), HX_LD, 128, s), "nchw_to_cl(inp)")
+
+    def net_nchw(self, ws):
+        out = torch.empty(ws.B, 128, ws.H8, ws.W8, dtype=torch.float32, device=ws.hx.device)
+        native.check(self.L.rnc_cl_to_nchw(_ptr(ws.hx), HX_LD, 0, ws.B, 128, ws.H8, ws.W8, _ptr(out), _stream()), "cl_to_nchw")
+        return out
+
+    def flow_low(self, ws):
+        out = torch.empty_like(ws.coords1)
+        native.check(self.L.rnc_coords_to_flow(_ptr(ws.coords1), _ptr(out), ws.B, ws.H8, ws.W8, _stream()), "coords_to_flow")
+        return out
+
+    # ------------------------------------------------------------------ upsamplers
+    def convex_upsample(self, ws, flow_low, mask_cl, ldm):
+        out = torch.empty(ws.B, 2, 8 * ws.H8, 8 * ws.W8, dtype=torch.float32, device=flow_low.device)
+        native.check(self.L.rnc_convex_upsample_fwd(_ptr(flow_low), _ptr(mask_cl), ldm, ws.B, ws.H8, ws.W8, _ptr(out),
+                                                    _stream()), "convex_upsample")
+        return out
+
+    def ncup_from_lowres(self, ws, pu, x_lowres, guid_ptr, ldg, out_scale):
+        """NConvUpsampler.forward (upsampler.py:143-177) on x_lowres NCHW [B,2,H4,W4] with CL guidance at H8."""
+        B, H8, W8 = ws.B, ws.H8, ws.W8
+        H4, W4 = 2 * H8, 2 * W8
+        s = _stream()
+        native.check(self.L.rnc_ncup_guidance_fwd(_ptr(x_lowres), C.c_void_p(guid_ptr), ldg, 128, B, H8, W8, _ptr(ws.gin),
+                                                  132, s), "ncup_guidance")
+        self.conv(B, H4, W4, ws.gin.data_ptr(), pu.cin0_pad, 132, pu.g0, pu.c_mid0, 3, 3, native.EPI_RELU, ws.g1.data_ptr(), 64)
+        self.conv(B, H4, W4, ws.g1.data_ptr(), pu.c_mid0, 64, pu.g1, pu.c_mid1, 3, 3, native.EPI_RELU, ws.g2.data_ptr(), 32)
+        native.check(self.L.rnc_conf_head_fwd(_ptr(ws.g2), pu.c_mid1, 32, _ptr(pu.gout[0]), _ptr(pu.gout[1]), B, H4, W4,
+                                              _ptr(ws.conf), s), "conf_head")
+        out = torch.empty(B, 2, 4 * H4, 4 * W4, dtype=torch.float32, device=x_lowres.device)
+        with _Timed(self, "ncup"):
+            native.check(self.L.rnc_ncup_fwd(_ptr(x_lowres), _ptr(ws.conf), pu.nconv_host, B, H4, W4, out_scale, _ptr(out), s), "ncup")
+        return out
