@@ -83,12 +83,25 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def host_cores():
+    """Cores this process may actually use: scheduler affinity capped by the cgroup CPU quota (the GPU boxes expose
+    128 logical CPUs but a 16-core quota; oversubscribing them makes the CPU path several times slower)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def cpu_oracle_pairs_per_s(steps, warmup):
     """The reference's algorithm on the host cores: oracle/raft_oracle.py (a torch-CPU restatement pinned to the reference
     by tests/golden).  One step = ONE pair at the full 1024x436 / 32-iteration shape (bounded sample of the 8-pair batch)."""
     from conftest import build_model
     from oracle import raft_oracle as orc
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(host_cores())
     sd = {k: v.detach() for k, v in build_model("raft_nc_dbl").state_dict().items()}
     p1, p2 = synth_frames(1, 7)
     for _ in range(warmup):

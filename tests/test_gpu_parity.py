@@ -176,14 +176,16 @@ def test_ncup_chain_non_multiple_of_tile(sd_ncup):
     eng = m.upsampler.engine()
     pu = eng.packed_upsampler(m.upsampler)
     out = torch.empty(2, 2, 88, 104, device=DEV)
-    native.check(eng.L.rnc_ncup_fwd(P(x.to(DEV)), P(c.to(DEV)), pu.nconv_host, 2, 22, 26, 8.0, P(out), stream()))
+    xd, cd = x.to(DEV), c.to(DEV)
+    native.check(eng.L.rnc_ncup_fwd(P(xd), P(cd), pu.nconv_host, 2, 22, 26, 8.0, P(out), stream()))
     assert (out.cpu() - 8 * ref.view(2, 2, 88, 104)).abs().max() < 1e-4
 
 
 def test_convex_upsampler_matches_reference_golden(gold):
     m = build_model("raft").to(DEV)
     out = m.upsample_flow(gold["convex_flow"].to(DEV), gold["convex_mask"].to(DEV))
-    assert (out.cpu() - gold["convex_out"]).abs().max() < 1e-5
+    ref = gold["convex_out"]
+    assert (out.cpu() - ref).abs().max() < 2e-6 * ref.abs().max()         # values reach ~40 px: 2e-6 relative
 
 
 # ----------------------------------------------------------------------------- end to end
