@@ -69,6 +69,12 @@ int rnc_corr_lookup_fwd(const float* f1_cl, const float* f2_pyr, const float* co
                         int B, int D, int H, int W, int levels, int radius,
                         float* out, int layout, int ldo, void* stream);
 
+/* Same lookup, written as exact fp16 hi/lo split planes (CL [B][H][W][ldo] halves each; value = hi + lo): the operand
+ * format of rnc_conv2d_umma_fwd, so the 1x1 convc1 (update.py:82,90) consumes it without a conversion pass. */
+int rnc_corr_lookup_split_fwd(const float* f1_cl, const float* f2_pyr, const float* coords,
+                              int B, int D, int H, int W, int levels, int radius,
+                              void* out_hi, void* out_lo, int ldo, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * A5..A8  update block convolutions  (core/update.py:6-14, 33-60, 79-97, 114-141)
  * One generic channel-last convolution with the update block's fusions expressed as epilogues.
@@ -101,10 +107,46 @@ typedef struct {
 
 int rnc_conv2d_cl_fwd(const rnc_conv_desc* desc, void* stream);
 
+/* Tensor-core version of rnc_conv2d_cl_fwd (same reference code, same epilogues): tcgen05.mma on fp16 hi/lo split
+ * operands with fp32 accumulation in TMEM (3 MMAs per K step: hi*hi + hi*lo + lo*hi), TMA-staged tiles.
+ * Activations live as two CL planes of halves (value = hi + lo); weights are pre-split and pre-scaled by a power of two:
+ *   w_hi/w_lo : [coutpad][ktot] halves, ktot = kh*kw * nblocks * 64, K index = (tap * nblocks + block) * 64 + c,
+ *               blocks enumerate 64-channel slices of segment 0 then segment 1, zero rows for channels beyond Cin
+ *   unscale   : 1 / (weight scale); out = act(acc * unscale + bias)
+ * Outputs: out_f32 (CL fp32) and/or out_hi/out_lo (CL split halves); either may be NULL.
+ *   GRU_ZR : z -> aux0 (fp32), r*h -> out_hi/out_lo;   GRU_Q : h (fp32, in place) and its split copy -> out_hi/out_lo
+ *   RELU_FLOW: split output, flow appended at channels [cout, cout+2); aux0 = coords1 NCHW
+ */
+typedef struct {
+  const void* in0_hi; const void* in0_lo; int c0; int ld0;
+  const void* in1_hi; const void* in1_lo; int c1; int ld1;
+  const void* w_hi; const void* w_lo; int ktot; int coutpad;
+  const float* bias; float unscale;
+  float* out_f32; int ldo_f32;
+  void* out_hi; void* out_lo; int ldo_split;
+  float* h; int ldh;
+  float* aux0; int ldaux;
+  int B, H, W;
+  int cout;
+  int kh, kw;
+  int epilogue;
+} rnc_conv_umma_desc;
+
+int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream);
+
+/* fp32 CL [M][lds] channels [0,C) -> split halves planes [M][ldd] at channel offset ch_off (hi + lo == value exactly
+ * when |value| <= 65504). */
+int rnc_f32_to_split(const float* src, int lds, int C, long long M, void* dst_hi, void* dst_lo, int ldd, int ch_off,
+                     void* stream);
+
 /* convf1: Conv2d(2,128,7,padding=3)+ReLU on flow = coords1 - coords0 (update.py:83,92).
  * coords1 NCHW [B][2][H][W]; weight packed [49][2][Cout]; out CL. */
 int rnc_conv_flow7x7_fwd(const float* coords1, const float* weight, const float* bias, int B, int H, int W,
                          int cout, float* out, int ldo, void* stream);
+
+/* convf1 with split-halves CL output (feeds the tensor-core convf2). */
+int rnc_conv_flow7x7_split_fwd(const float* coords1, const float* weight, const float* bias, int B, int H, int W,
+                               int cout, void* out_hi, void* out_lo, int ldo, void* stream);
 
 /* FlowHead.conv2 (update.py:10,14) fused with `coords1 = coords1 + delta_flow` (raft_nc_dbl.py:157):
  * in CL [B][H][W][cin]; weight packed [9][cin][2]; delta (optional, may be NULL) and coords1 NCHW [B][2][H][W]. */

@@ -11,6 +11,7 @@
 // union bounding box of the tile's windows (16 channels at a time) in shared memory and every thread
 // accumulates 25 of its pixel's 100 lattice dot products; tiles whose box does not fit fall back to
 // direct global loads.
+#include <cuda_fp16.h>
 #include "rnc_common.cuh"
 
 namespace rnc {
@@ -48,7 +49,7 @@ __device__ __forceinline__ float dot16(const float (&a)[kChunk], const float* __
 __global__ void __launch_bounds__(kThreads, 2)
 corr_lookup_tile_kernel(const float* __restrict__ f1_cl, const float* __restrict__ f2_pyr,
                         const float* __restrict__ coords, int B, int D, int H, int W, int levels,
-                        float* __restrict__ out, int layout, int ldo) {
+                        float* __restrict__ out, int layout, int ldo, __half* __restrict__ out_lo) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LookupSmem& sm = *reinterpret_cast<LookupSmem*>(smem_raw);
 
@@ -172,8 +173,15 @@ corr_lookup_tile_kernel(const float* __restrict__ f1_cl, const float* __restrict
       const float v = (1.f - ax) * (1.f - ay) * g[0] + ax * (1.f - ay) * g[kG] + (1.f - ax) * ay * g[1] + ax * ay * g[kG + 1];
       if (layout == 0)
         out[(((size_t)b * K + l * kS * kS + k) * H + qy) * W + qx] = v;
-      else
+      else if (layout == 1)
         out[((size_t)b * P + qy * W + qx) * ldo + l * kS * kS + k] = v;
+      else {   // layout 2: exact hi/lo split halves planes (input format of the tcgen05 convolutions)
+        const size_t idx = ((size_t)b * P + qy * W + qx) * ldo + l * kS * kS + k;
+        const float vc = fminf(fmaxf(v, -65504.f), 65504.f);
+        const __half hi = __float2half_rn(vc);
+        reinterpret_cast<__half*>(out)[idx] = hi;
+        out_lo[idx] = __float2half_rn(vc - __half2float(hi));
+      }
     }
     __syncthreads();
   }
@@ -183,19 +191,34 @@ corr_lookup_tile_kernel(const float* __restrict__ f1_cl, const float* __restrict
 
 using namespace rnc;
 
-extern "C" int rnc_corr_lookup_fwd(const float* f1_cl, const float* f2_pyr, const float* coords,
-                                   int B, int D, int H, int W, int levels, int radius,
-                                   float* out, int layout, int ldo, void* stream) {
+static int lookup_launch(const float* f1_cl, const float* f2_pyr, const float* coords,
+                         int B, int D, int H, int W, int levels, int radius,
+                         float* out, int layout, int ldo, __half* out_lo, void* stream) {
   if (B <= 0 || H <= 0 || W <= 0 || D <= 0 || (D % kChunk) != 0) return RNC_ERR_BAD_SHAPE;
   if (levels < 1 || levels > 4 || (H >> (levels - 1)) < 1 || (W >> (levels - 1)) < 1) return RNC_ERR_BAD_SHAPE;
   if (radius != kR) return RNC_ERR_UNSUPPORTED;
-  if (layout != 0 && layout != 1) return RNC_ERR_BAD_SHAPE;
-  if (layout == 1 && ldo < levels * kS * kS) return RNC_ERR_BAD_SHAPE;
+  if (layout < 0 || layout > 2) return RNC_ERR_BAD_SHAPE;
+  if (layout >= 1 && ldo < levels * kS * kS) return RNC_ERR_BAD_SHAPE;
+  if (layout == 2 && !out_lo) return RNC_ERR_BAD_POINTER;
   if (!f1_cl || !f2_pyr || !coords || !out || !aligned16(f1_cl) || !aligned16(f2_pyr)) return RNC_ERR_BAD_POINTER;
   static unsigned long long attr_done = 0;
   if (int st = ensure_dyn_smem(corr_lookup_tile_kernel, (int)sizeof(LookupSmem), &attr_done)) return st;
   dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, B);
   corr_lookup_tile_kernel<<<grid, kThreads, sizeof(LookupSmem), as_stream(stream)>>>(
-      f1_cl, f2_pyr, coords, B, D, H, W, levels, out, layout, ldo);
+      f1_cl, f2_pyr, coords, B, D, H, W, levels, out, layout, ldo, out_lo);
   return after_launch();
+}
+
+extern "C" int rnc_corr_lookup_fwd(const float* f1_cl, const float* f2_pyr, const float* coords,
+                                   int B, int D, int H, int W, int levels, int radius,
+                                   float* out, int layout, int ldo, void* stream) {
+  if (layout != 0 && layout != 1) return RNC_ERR_BAD_SHAPE;
+  return lookup_launch(f1_cl, f2_pyr, coords, B, D, H, W, levels, radius, out, layout, ldo, nullptr, stream);
+}
+
+extern "C" int rnc_corr_lookup_split_fwd(const float* f1_cl, const float* f2_pyr, const float* coords,
+                                         int B, int D, int H, int W, int levels, int radius,
+                                         void* out_hi, void* out_lo, int ldo, void* stream) {
+  return lookup_launch(f1_cl, f2_pyr, coords, B, D, H, W, levels, radius, static_cast<float*>(out_hi), 2, ldo,
+                       static_cast<__half*>(out_lo), stream);
 }

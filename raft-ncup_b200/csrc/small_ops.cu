@@ -4,6 +4,7 @@
 //   conf_head    : Simple.out + sigmoid (core/interp_weights_est.py:37,47; core/upsampler.py:44-46)
 //   ncup_guidance: nearest-x2 of flow and of the guidance (raft_nc_dbl.py:110, upsampler.py:150,155)
 //   convex       : RAFT.upsample_flow (core/raft.py:73-84)
+#include <cuda_fp16.h>
 #include "rnc_common.cuh"
 
 namespace rnc {
@@ -12,7 +13,8 @@ namespace rnc {
 constexpr int F7_PX = 16;   // pixels (along x) per CTA
 __global__ void __launch_bounds__(128)
 conv_flow7x7_kernel(const float* __restrict__ coords1, const float* __restrict__ weight, const float* __restrict__ bias,
-                    int B, int H, int W, int cout, float* __restrict__ out, int ldo) {
+                    int B, int H, int W, int cout, float* __restrict__ out, int ldo, __half* __restrict__ out_hi,
+                    __half* __restrict__ out_lo) {
   __shared__ float patch[2][7][F7_PX + 6];
   const int b = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * F7_PX;
   const int HW = H * W;
@@ -44,7 +46,17 @@ conv_flow7x7_kernel(const float* __restrict__ coords1, const float* __restrict__
       }
 #pragma unroll
     for (int i = 0; i < F7_PX; ++i)
-      if (x0 + i < W) out[((size_t)b * HW + y * W + x0 + i) * ldo + co] = fmaxf(acc[i], 0.f);
+      if (x0 + i < W) {
+        const size_t idx = ((size_t)b * HW + y * W + x0 + i) * ldo + co;
+        const float v = fmaxf(acc[i], 0.f);
+        if (out) out[idx] = v;
+        if (out_hi) {
+          const float vc = fminf(v, 65504.f);
+          const __half hi = __float2half_rn(vc);
+          out_hi[idx] = hi;
+          out_lo[idx] = __float2half_rn(vc - __half2float(hi));
+        }
+      }
   }
 }
 
@@ -138,6 +150,20 @@ __global__ void ncup_guidance_kernel(const float* __restrict__ x_lowres, const f
   }
 }
 
+// ---------------------------------------------------------------- fp32 CL -> exact hi/lo halves planes
+__global__ void f32_to_split_kernel(const float* __restrict__ src, int lds, int C, long long M, __half* __restrict__ hi,
+                                    __half* __restrict__ lo, int ldd, int ch_off) {
+  const long long n = M * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / C;
+    const int c = (int)(i - m * C);
+    const float v = fminf(fmaxf(src[m * lds + c], -65504.f), 65504.f);
+    const __half h = __float2half_rn(v);
+    hi[m * ldd + ch_off + c] = h;
+    lo[m * ldd + ch_off + c] = __float2half_rn(v - __half2float(h));
+  }
+}
+
 // ---------------------------------------------------------------- convex upsampling (raft.py:73-84)
 __global__ void __launch_bounds__(256)
 convex_upsample_kernel(const float* __restrict__ flow, const float* __restrict__ mask, int ldm, int B, int H8, int W8,
@@ -187,7 +213,17 @@ int rnc_conv_flow7x7_fwd(const float* coords1, const float* weight, const float*
   if (B <= 0 || H <= 0 || W <= 0 || cout <= 0 || ldo < cout) return RNC_ERR_BAD_SHAPE;
   if (!coords1 || !weight || !bias || !out) return RNC_ERR_BAD_POINTER;
   dim3 grid((W + F7_PX - 1) / F7_PX, H, B);
-  conv_flow7x7_kernel<<<grid, 128, 0, as_stream(stream)>>>(coords1, weight, bias, B, H, W, cout, out, ldo);
+  conv_flow7x7_kernel<<<grid, 128, 0, as_stream(stream)>>>(coords1, weight, bias, B, H, W, cout, out, ldo, nullptr, nullptr);
+  return after_launch();
+}
+
+int rnc_conv_flow7x7_split_fwd(const float* coords1, const float* weight, const float* bias, int B, int H, int W,
+                               int cout, void* out_hi, void* out_lo, int ldo, void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0 || cout <= 0 || ldo < cout) return RNC_ERR_BAD_SHAPE;
+  if (!coords1 || !weight || !bias || !out_hi || !out_lo) return RNC_ERR_BAD_POINTER;
+  dim3 grid((W + F7_PX - 1) / F7_PX, H, B);
+  conv_flow7x7_kernel<<<grid, 128, 0, as_stream(stream)>>>(coords1, weight, bias, B, H, W, cout, nullptr, ldo,
+                                                           static_cast<__half*>(out_hi), static_cast<__half*>(out_lo));
   return after_launch();
 }
 
@@ -210,6 +246,17 @@ int rnc_conf_head_fwd(const float* in, int cin, int ldi, const float* weight, co
   const int M = B * H4 * W4;
   int blocks = (M + 255) / 256;
   conf_head_kernel<<<blocks, 256, 0, as_stream(stream)>>>(in, cin, ldi, weight, bias, B, H4 * W4, conf);
+  return after_launch();
+}
+
+int rnc_f32_to_split(const float* src, int lds, int C, long long M, void* dst_hi, void* dst_lo, int ldd, int ch_off,
+                     void* stream) {
+  if (C <= 0 || M <= 0 || lds < C || ldd < C + ch_off || ch_off < 0) return RNC_ERR_BAD_SHAPE;
+  if (!src || !dst_hi || !dst_lo) return RNC_ERR_BAD_POINTER;
+  long long blocks = (M * C + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  f32_to_split_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(src, lds, C, M, static_cast<__half*>(dst_hi),
+                                                                 static_cast<__half*>(dst_lo), ldd, ch_off);
   return after_launch();
 }
 

@@ -161,8 +161,22 @@ class _Timed:
         return False
 
 
+def make_engine():
+    """RNC_CONV=umma (default): tcgen05 tensor-core convolutions on fp16 hi/lo split operands;
+    RNC_CONV=ffma: exact-fp32 CUDA-core convolutions (v1, kept as the on-GPU cross-check)."""
+    import os
+    mode = os.environ.get("RNC_CONV", "umma").lower()
+    if mode == "ffma":
+        return Engine()
+    if mode == "umma":
+        from .engine_umma import UmmaEngine
+        return UmmaEngine()
+    raise ValueError(f"RNC_CONV={mode!r}: expected 'umma' or 'ffma'")
+
+
 class Engine:
     """Issues the kernels.  One per model instance; keeps packed weights and workspaces."""
+    mode = "ffma"
 
     def __init__(self):
         self.profile = None
@@ -223,6 +237,18 @@ class Engine:
         with _Timed(self, "corr_lookup"):
             native.check(self.L.rnc_corr_lookup_fwd(_ptr(ws.f1_cl), _ptr(ws.f2_pyr), _ptr(coords), ws.B, ws.D, ws.H8, ws.W8,
                                                     ws.levels, radius, _ptr(out), layout, ldo, _stream()), "corr_lookup")
+
+    def lookup_resident(self, ws):
+        """Per-iteration lookup at ws.coords1 into the resident corr buffer (CL fp32)."""
+        self.lookup(ws, ws.coords1, ws.corr, 1, CORR_CH)
+
+    def load_corr(self, ws, corr_nchw):
+        B, _, H, W = corr_nchw.shape
+        native.check(self.L.rnc_nchw_to_cl(_ptr(corr_nchw), B, CORR_CH, H, W, _ptr(ws.corr), CORR_CH, 0, _stream()), "nchw_to_cl(corr)")
+
+    def guidance(self, ws):
+        """(pointer, pixel stride) of the CL fp32 hidden state used as NCUP guidance (update.py:135, raft_nc_dbl.py:161)."""
+        return ws.hx.data_ptr(), HX_LD
 
     # ------------------------------------------------------------------ update block on resident buffers
     def update_iter(self, ws, pk, want_mask=False, want_delta=False):

@@ -1,0 +1,256 @@
+"""Tensor-core variant of rnc.engine: the same loop body (raft_nc_dbl.py:148-165, update.py:130-141), with every
+wide convolution on tcgen05 (rnc_conv2d_umma_fwd) and the 1/8-resolution activations resident as fp16 hi/lo split
+planes (value = hi + lo).  Thin layers (7x7 on flow, 3x3 -> 2 flow head, 1x1 -> 2 confidence head) stay on CUDA cores.
+"""
+import ctypes as C
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import native
+from .engine import CORR_CH, HX_LD, Engine, PackedUpsampler, _ptr, _stream, _Timed, pack_thin
+from .native import UmmaConvDesc
+
+CORR_LD = 328          # 324 padded so that the row pitch of the halves planes is a multiple of 16 B
+GIN_LD = 136           # 2 + 128 (+2 zero) channels of the weights-net input, pitch multiple of 16 B
+
+
+def _coutpad(cout):
+    for c in (32, 64, 128, 192, 256):
+        if cout <= c:
+            return c
+    return (cout + 191) // 192 * 192
+
+
+class UmmaWeights:
+    """[Cout,Cin,KH,KW] -> hi/lo halves planes [CoutPad][taps * blocks * 64] scaled by 2^s (s chosen so the largest
+    weight lands in [512, 1024): w_lo then stays a normal half) + fp32 bias [CoutPad] + unscale = 2^-s."""
+
+    def __init__(self, weight, bias, segs, extra_cout=0, out_scale=1.0):
+        cout, cin, kh, kw = weight.shape
+        w = weight.detach().float() * out_scale
+        nblks = [(c + 63) // 64 for c in segs]
+        nblk = sum(nblks)
+        self.cout, self.kh, self.kw = cout, kh, kw
+        self.coutpad = _coutpad(cout + extra_cout)
+        self.ktot = kh * kw * nblk * 64
+        wp = torch.zeros(self.coutpad, kh * kw, nblk * 64, dtype=torch.float32, device=w.device)
+        ci = col = 0
+        for c, nb in zip(segs, nblks):
+            take = min(c, cin - ci)
+            if take > 0:
+                wp[:cout, :, col:col + take] = w[:, ci:ci + take].permute(0, 2, 3, 1).reshape(cout, kh * kw, take)
+            ci += take
+            col += nb * 64
+        assert ci == cin, "segments do not cover the weight's input channels"
+        mx = float(wp.abs().max())
+        s = math.floor(math.log2(1000.0 / mx)) if mx > 0 else 0
+        ws = wp.reshape(self.coutpad, self.ktot) * (2.0 ** s)
+        self.w_hi = ws.half().contiguous()
+        self.w_lo = (ws - self.w_hi.float()).half().contiguous()
+        self.unscale = 2.0 ** (-s)
+        self.bias = torch.zeros(self.coutpad, dtype=torch.float32, device=w.device)
+        if bias is not None:
+            self.bias[:cout] = bias.detach().float() * out_scale
+
+
+class PackedUpdateUmma:
+    def __init__(self, ub):
+        e, g, fh = ub.encoder, ub.gru, ub.flow_head
+        cat = torch.cat
+        self.convc1 = UmmaWeights(e.convc1.weight, e.convc1.bias, [CORR_CH])
+        self.convc2 = UmmaWeights(e.convc2.weight, e.convc2.bias, [256])
+        self.convf1 = (pack_thin(e.convf1.weight), e.convf1.bias.detach().float().contiguous())
+        self.convf2 = UmmaWeights(e.convf2.weight, e.convf2.bias, [128])
+        self.conv = UmmaWeights(e.conv.weight, e.conv.bias, [256], extra_cout=2)
+        self.zr1 = UmmaWeights(cat([g.convz1.weight, g.convr1.weight], 0), cat([g.convz1.bias, g.convr1.bias], 0), [HX_LD])
+        self.q1 = UmmaWeights(g.convq1.weight, g.convq1.bias, [128, 256])
+        self.zr2 = UmmaWeights(cat([g.convz2.weight, g.convr2.weight], 0), cat([g.convz2.bias, g.convr2.bias], 0), [HX_LD])
+        self.q2 = UmmaWeights(g.convq2.weight, g.convq2.bias, [128, 256])
+        self.fh1 = UmmaWeights(fh.conv1.weight, fh.conv1.bias, [128])
+        self.fh2 = (pack_thin(fh.conv2.weight), fh.conv2.bias.detach().float().contiguous())
+        self.has_mask = len(ub.mask) > 0
+        if self.has_mask:
+            self.m0 = UmmaWeights(ub.mask[0].weight, ub.mask[0].bias, [128])
+            self.m2 = UmmaWeights(ub.mask[2].weight, ub.mask[2].bias, [256], out_scale=0.25)   # update.py:140
+
+
+class PackedUpsamplerUmma(PackedUpsampler):
+    def __init__(self, up):
+        super().__init__(up)
+        # re-pack the BN-folded 3x3 layers of the weights net for the tensor-core path
+        wn = up.weights_est_net
+        convs = []
+        for blk in wn.conv:
+            w, b = blk[0].weight.detach().float(), blk[0].bias.detach().float()
+            if len(blk) == 3:
+                bn = blk[1]
+                s = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+                w, b = w * s.view(-1, 1, 1, 1), (b - bn.running_mean) * s + bn.bias.detach()
+            convs.append((w, b))
+        self.u0 = UmmaWeights(convs[0][0], convs[0][1], [132])
+        self.u1 = UmmaWeights(convs[1][0], convs[1][1], [64])
+
+
+class SplitBuf:
+    """A CL activation stored as two planes of halves."""
+
+    def __init__(self, rows, ld, device):
+        self.hi = torch.zeros(rows, ld, dtype=torch.float16, device=device)
+        self.lo = torch.zeros(rows, ld, dtype=torch.float16, device=device)
+        self.ld = ld
+
+    def ptrs(self, ch_off=0):
+        return self.hi.data_ptr() + 2 * ch_off, self.lo.data_ptr() + 2 * ch_off
+
+
+class UmmaWorkspace:
+    def __init__(self, device, B, H8, W8, with_mask, with_ncup):
+        self.B, self.H8, self.W8 = B, H8, W8
+        M = B * H8 * W8
+        f = dict(dtype=torch.float32, device=device)
+        self.corr = SplitBuf(M, CORR_LD, device)
+        self.c1 = SplitBuf(M, 256, device)
+        self.corflo = SplitBuf(M, 256, device)
+        self.f1 = SplitBuf(M, 128, device)
+        self.hx = SplitBuf(M, HX_LD, device)
+        self.rh = SplitBuf(M, 128, device)
+        self.h = torch.zeros(M, 128, **f)            # fp32 master copy of the GRU state
+        self.z = torch.empty(M, 128, **f)
+        self.fh = torch.empty(M, 256, **f)
+        self.tmp = torch.empty(M, 256, **f)
+        self.coords1 = torch.empty(B, 2, H8, W8, **f)
+        self.delta = torch.empty(B, 2, H8, W8, **f)
+        self.f1_cl = self.f2_pyr = None
+        if with_mask:
+            self.mh = SplitBuf(M, 256, device)
+            self.mask = torch.empty(M, 576, **f)
+        if with_ncup:
+            M4 = 4 * M
+            self.x4 = torch.empty(B, 2, 2 * H8, 2 * W8, **f)
+            self.gin32 = torch.empty(M4, 132, **f)
+            self.gin = SplitBuf(M4, GIN_LD, device)
+            self.g1 = SplitBuf(M4, 64, device)
+            self.g2 = torch.empty(M4, 32, **f)
+            self.conf = torch.empty(B, 2, 2 * H8, 2 * W8, **f)
+
+
+class UmmaEngine(Engine):
+    mode = "umma"
+
+    def packed_update(self, ub):
+        from .engine import _param_key
+        key = _param_key(ub)
+        if key != self._ub_key:
+            self._packed_ub, self._ub_key = PackedUpdateUmma(ub), key
+        return self._packed_ub
+
+    def packed_upsampler(self, up):
+        from .engine import _param_key
+        key = _param_key(up)
+        if key != self._up_key:
+            self._packed_up, self._up_key = PackedUpsamplerUmma(up), key
+        return self._packed_up
+
+    def workspace(self, device, B, H8, W8, with_mask, with_ncup):
+        key = ("umma", str(device), B, H8, W8, with_mask, with_ncup)
+        ws = self._ws.get(key)
+        if ws is None:
+            if len(self._ws) >= 4:
+                self._ws.clear()
+            ws = self._ws[key] = UmmaWorkspace(device, B, H8, W8, with_mask, with_ncup)
+        return ws
+
+    # ------------------------------------------------------------------ one tensor-core convolution
+    def uconv(self, B, H, W, in0, c0, ld0, wt, epi, out_f32=0, ldo_f32=0, out_split=(0, 0), ldo_split=0, in1=(0, 0), c1=0, ld1=0,
+              h=0, ldh=0, aux0=0, ldaux=0):
+        d = UmmaConvDesc()
+        d.in0_hi, d.in0_lo, d.c0, d.ld0 = in0[0], in0[1], c0, ld0
+        d.in1_hi, d.in1_lo, d.c1, d.ld1 = in1[0], in1[1], c1, ld1
+        d.w_hi, d.w_lo, d.ktot, d.coutpad = wt.w_hi.data_ptr(), wt.w_lo.data_ptr(), wt.ktot, wt.coutpad
+        d.bias, d.unscale = wt.bias.data_ptr(), wt.unscale
+        d.out_f32, d.ldo_f32 = out_f32, ldo_f32
+        d.out_hi, d.out_lo, d.ldo_split = out_split[0], out_split[1], ldo_split
+        d.h, d.ldh, d.aux0, d.ldaux = h, ldh, aux0, ldaux
+        d.B, d.H, d.W = B, H, W
+        d.cout, d.kh, d.kw, d.epilogue = wt.cout, wt.kh, wt.kw, epi
+        native.check(self.L.rnc_conv2d_umma_fwd(C.byref(d), _stream()), "conv2d_umma")
+
+    def lookup_resident(self, ws):
+        """corr lookup straight into the split planes convc1 consumes."""
+        with _Timed(self, "corr_lookup"):
+            native.check(self.L.rnc_corr_lookup_split_fwd(_ptr(ws.f1_cl), _ptr(ws.f2_pyr), _ptr(ws.coords1), ws.B, ws.D, ws.H8,
+                                                          ws.W8, ws.levels, 4, _ptr(ws.corr.hi), _ptr(ws.corr.lo), CORR_LD,
+                                                          _stream()), "corr_lookup_split")
+
+    def _update_iter(self, ws, pk, want_mask, want_delta):
+        B, H, W = ws.B, ws.H8, ws.W8
+        s = _stream()
+        E = native
+        # BasicMotionEncoder (update.py:89-97)
+        self.uconv(B, H, W, ws.corr.ptrs(), CORR_CH, CORR_LD, pk.convc1, E.EPI_RELU, out_split=ws.c1.ptrs(), ldo_split=256)
+        self.uconv(B, H, W, ws.c1.ptrs(), 256, 256, pk.convc2, E.EPI_RELU, out_split=ws.corflo.ptrs(), ldo_split=256)
+        native.check(self.L.rnc_conv_flow7x7_split_fwd(_ptr(ws.coords1), _ptr(pk.convf1[0]), _ptr(pk.convf1[1]), B, H, W, 128,
+                                                       _ptr(ws.f1.hi), _ptr(ws.f1.lo), 128, s), "convf1")
+        self.uconv(B, H, W, ws.f1.ptrs(), 128, 128, pk.convf2, E.EPI_RELU, out_split=ws.corflo.ptrs(192), ldo_split=256)
+        self.uconv(B, H, W, ws.corflo.ptrs(), 256, 256, pk.conv, E.EPI_RELU_FLOW, out_split=ws.hx.ptrs(256), ldo_split=HX_LD,
+                   aux0=ws.coords1.data_ptr())
+        # SepConvGRU (update.py:45-60)
+        hp = ws.h.data_ptr()
+        for zr, q in ((pk.zr1, pk.q1), (pk.zr2, pk.q2)):
+            self.uconv(B, H, W, ws.hx.ptrs(), HX_LD, HX_LD, zr, E.EPI_GRU_ZR, out_split=ws.rh.ptrs(), ldo_split=128,
+                       h=hp, ldh=128, aux0=ws.z.data_ptr(), ldaux=128)
+            self.uconv(B, H, W, ws.rh.ptrs(), 128, 128, q, E.EPI_GRU_Q, in1=ws.hx.ptrs(128), c1=256, ld1=HX_LD,
+                       out_split=ws.hx.ptrs(), ldo_split=HX_LD, h=hp, ldh=128, aux0=ws.z.data_ptr(), ldaux=128)
+        # FlowHead (update.py:13-14) + coords1 += delta (raft_nc_dbl.py:157)
+        self.uconv(B, H, W, ws.hx.ptrs(), 128, HX_LD, pk.fh1, E.EPI_RELU, out_f32=ws.fh.data_ptr(), ldo_f32=256)
+        native.check(self.L.rnc_flow_head2_fwd(_ptr(ws.fh), 256, 256, _ptr(pk.fh2[0]), _ptr(pk.fh2[1]), B, H, W,
+                                               _ptr(ws.delta) if want_delta else C.c_void_p(0), _ptr(ws.coords1), s), "flow_head2")
+        if want_mask:
+            self.uconv(B, H, W, ws.hx.ptrs(), 128, HX_LD, pk.m0, E.EPI_RELU, out_split=ws.mh.ptrs(), ldo_split=256)
+            self.uconv(B, H, W, ws.mh.ptrs(), 256, 256, pk.m2, E.EPI_LINEAR, out_f32=ws.mask.data_ptr(), ldo_f32=576)
+
+    def load_state(self, ws, net, inp):
+        B, _, H, W = net.shape
+        s = _stream()
+        M = B * H * W
+        L = self.L
+        native.check(L.rnc_nchw_to_cl(_ptr(net), B, 128, H, W, _ptr(ws.h), 128, 0, s), "nchw_to_cl(net)")
+        native.check(L.rnc_nchw_to_cl(_ptr(net), B, 128, H, W, _ptr(ws.tmp), 256, 0, s), "nchw_to_cl(net)")
+        native.check(L.rnc_nchw_to_cl(_ptr(inp), B, 128, H, W, _ptr(ws.tmp), 256, 128, s), "nchw_to_cl(inp)")
+        native.check(L.rnc_f32_to_split(_ptr(ws.tmp), 256, 256, M, _ptr(ws.hx.hi), _ptr(ws.hx.lo), HX_LD, 0, s), "f32_to_split")
+
+    def load_corr(self, ws, corr_nchw):
+        """seam path (BasicUpdateBlock.forward): NCHW corr -> split planes."""
+        B, _, H, W = corr_nchw.shape
+        tmp = torch.empty(B * H * W, CORR_CH, dtype=torch.float32, device=corr_nchw.device)
+        native.check(self.L.rnc_nchw_to_cl(_ptr(corr_nchw), B, CORR_CH, H, W, _ptr(tmp), CORR_CH, 0, _stream()), "nchw_to_cl(corr)")
+        native.check(self.L.rnc_f32_to_split(_ptr(tmp), CORR_CH, CORR_CH, B * H * W, _ptr(ws.corr.hi), _ptr(ws.corr.lo), CORR_LD, 0,
+                                             _stream()), "f32_to_split(corr)")
+
+    def net_nchw(self, ws):
+        out = torch.empty(ws.B, 128, ws.H8, ws.W8, dtype=torch.float32, device=ws.h.device)
+        native.check(self.L.rnc_cl_to_nchw(_ptr(ws.h), 128, 0, ws.B, 128, ws.H8, ws.W8, _ptr(out), _stream()), "cl_to_nchw")
+        return out
+
+    def guidance(self, ws):
+        return ws.h.data_ptr(), 128
+
+    def ncup_from_lowres(self, ws, pu, x_lowres, guid_ptr, ldg, out_scale):
+        B, H8, W8 = ws.B, ws.H8, ws.W8
+        H4, W4 = 2 * H8, 2 * W8
+        M4 = B * H4 * W4
+        s = _stream()
+        L = self.L
+        native.check(L.rnc_ncup_guidance_fwd(_ptr(x_lowres), C.c_void_p(guid_ptr), ldg, 128, B, H8, W8, _ptr(ws.gin32), 132, s),
+                     "ncup_guidance")
+        native.check(L.rnc_f32_to_split(_ptr(ws.gin32), 132, 132, M4, _ptr(ws.gin.hi), _ptr(ws.gin.lo), GIN_LD, 0, s), "f32_to_split")
+        self.uconv(B, H4, W4, ws.gin.ptrs(), 132, GIN_LD, pu.u0, native.EPI_RELU, out_split=ws.g1.ptrs(), ldo_split=64)
+        self.uconv(B, H4, W4, ws.g1.ptrs(), 64, 64, pu.u1, native.EPI_RELU, out_f32=ws.g2.data_ptr(), ldo_f32=32)
+        native.check(L.rnc_conf_head_fwd(_ptr(ws.g2), pu.c_mid1, 32, _ptr(pu.gout[0]), _ptr(pu.gout[1]), B, H4, W4, _ptr(ws.conf), s),
+                     "conf_head")
+        out = torch.empty(B, 2, 4 * H4, 4 * W4, dtype=torch.float32, device=x_lowres.device)
+        with _Timed(self, "ncup"):
+            native.check(L.rnc_ncup_fwd(_ptr(x_lowres), _ptr(ws.conf), pu.nconv_host, B, H4, W4, out_scale, _ptr(out), s), "ncup")
+        return out

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from . import native
-from .engine import CORR_CH, HX_LD, Engine, _ptr, _require_cuda, _stream
+from .engine import _ptr, _require_cuda, _stream, make_engine
 from .modules import BasicEncoder, BasicUpdateBlock, get_upsampler
 
 
@@ -48,7 +48,7 @@ class _RAFTBase(nn.Module):
 
     def engine(self):
         if self._eng is None:
-            self._eng = Engine()
+            self._eng = make_engine()
         return self._eng
 
     # ------------------------------------------------------------------ forward
@@ -101,7 +101,7 @@ class _RAFTBase(nn.Module):
         for itr in range(iters):
             last = itr == iters - 1
             need_up = last or not test_mode     # inference upsamples once (SURVEY.md finding 9); list mode needs all
-            eng.lookup(ws, ws.coords1, ws.corr, 1, CORR_CH)
+            eng.lookup_resident(ws)
             eng.update_iter(ws, pk, want_mask=(pk.has_mask and need_up))
             if need_up:
                 flow_up = self._upsample(eng, ws, pu)
@@ -153,7 +153,8 @@ class RAFTNcup(_RAFTBase):
 
     def _upsample(self, eng, ws, pu):
         native.check(eng.L.rnc_flow_x2_fwd(_ptr(ws.coords1), ws.B, ws.H8, ws.W8, _ptr(ws.x4), _stream()), "flow_x2")
-        return eng.ncup_from_lowres(ws, pu, ws.x4, ws.hx.data_ptr(), HX_LD, 8.0)   # `8 *` of raft_nc_dbl.py:161
+        gptr, gld = eng.guidance(ws)
+        return eng.ncup_from_lowres(ws, pu, ws.x4, gptr, gld, 8.0)   # `8 *` of raft_nc_dbl.py:161
 
     def upsample_flow(self, flow_lr, guidance):
         """raft_nc_dbl.py:107-112 (without the caller's x8): nearest x2, then the NConv upsampler."""

@@ -14,7 +14,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import native
-from .engine import CORR_CH, HX_LD, Engine, _ptr, _require_cuda, _stream
+from .engine import CORR_CH, _ptr, _require_cuda, _stream, make_engine
 
 # --------------------------------------------------------------------------------------------- encoders (C6)
 # Run once per pair, outside the per-iteration path: kept on cuDNN in strict fp32 (SURVEY.md §8f-1 "next").
@@ -98,7 +98,7 @@ class CorrBlock:
     def __init__(self, fmap1, fmap2, num_levels=4, radius=4, engine=None):
         _require_cuda(fmap1, fmap2)
         self.num_levels, self.radius = num_levels, radius
-        self.engine = engine or Engine()
+        self.engine = engine or make_engine()
         B, D, H, W = fmap1.shape
         self.ws = _LookupState(B, D, H, W)
         self.engine.fmap_prepare(self.ws, fmap1.detach().float().contiguous(), fmap2.detach().float().contiguous(), num_levels)
@@ -169,7 +169,7 @@ class BasicUpdateBlock(nn.Module):
 
     def engine(self):
         if self._engine is None:
-            self._engine = Engine()
+            self._engine = make_engine()
         return self._engine
 
     def forward(self, net, inp, corr, flow, upsample=True):
@@ -183,7 +183,7 @@ class BasicUpdateBlock(nn.Module):
         s = _stream()
         L = eng.L
         eng.load_state(ws, net.float().contiguous(), inp.float().contiguous())
-        native.check(L.rnc_nchw_to_cl(_ptr(corr.float().contiguous()), B, CORR_CH, H, W, _ptr(ws.corr), CORR_CH, 0, s), "nchw_to_cl(corr)")
+        eng.load_corr(ws, corr.float().contiguous())
         # the kernels read flow as coords1 - grid: rebuild coords1 from the flow argument
         native.check(L.rnc_coords_init(_ptr(ws.coords1), _ptr(flow.float().contiguous()), B, H, W, s), "coords_init")
         eng.update_iter(ws, pk, want_mask=pk.has_mask, want_delta=True)
@@ -282,7 +282,7 @@ class NConvUpsampler(nn.Module):
 
     def engine(self):
         if self._engine is None:
-            self._engine = Engine()
+            self._engine = make_engine()
         return self._engine
 
     def forward(self, x_lowres, x_guidance=None, out_scale=1.0):

@@ -37,6 +37,20 @@ class ConvDesc(C.Structure):
                 ("cout", _i), ("kh", _i), ("kw", _i), ("epilogue", _i)]
 
 
+class UmmaConvDesc(C.Structure):
+    """Mirror of rnc_conv_umma_desc (include/rnc.h)."""
+    _fields_ = [("in0_hi", _vp), ("in0_lo", _vp), ("c0", _i), ("ld0", _i),
+                ("in1_hi", _vp), ("in1_lo", _vp), ("c1", _i), ("ld1", _i),
+                ("w_hi", _vp), ("w_lo", _vp), ("ktot", _i), ("coutpad", _i),
+                ("bias", _vp), ("unscale", _f),
+                ("out_f32", _vp), ("ldo_f32", _i),
+                ("out_hi", _vp), ("out_lo", _vp), ("ldo_split", _i),
+                ("h", _vp), ("ldh", _i),
+                ("aux0", _vp), ("ldaux", _i),
+                ("B", _i), ("H", _i), ("W", _i),
+                ("cout", _i), ("kh", _i), ("kw", _i), ("epilogue", _i)]
+
+
 # name -> (restype, argtypes); every symbol include/rnc.h declares
 SIGNATURES = {
     "rnc_abi_version": (_i, []),
@@ -48,7 +62,11 @@ SIGNATURES = {
     "rnc_pyramid_offset": (C.c_size_t, [_i, _i, _i, _i, _i]),
     "rnc_fmap_prepare": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rnc_corr_lookup_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
+    "rnc_corr_lookup_split_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "rnc_conv2d_cl_fwd": (_i, [C.POINTER(ConvDesc), _vp]),
+    "rnc_conv2d_umma_fwd": (_i, [C.POINTER(UmmaConvDesc), _vp]),
+    "rnc_f32_to_split": (_i, [_vp, _i, _i, C.c_longlong, _vp, _vp, _i, _i, _vp]),
+    "rnc_conv_flow7x7_split_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "rnc_conv_flow7x7_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "rnc_flow_head2_fwd": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "rnc_coords_init": (_i, [_vp, _vp, _i, _i, _i, _vp]),

@@ -1,0 +1,143 @@
+"""GPU parity of the tcgen05 (tensor-core) convolution path against fp32 references: the fp16 hi/lo split must stay
+fp32-faithful (north star: 1e-3 EPE after 32 recurrent iterations; plain TF32/bf16 operands fail it)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import build_model, frames
+from oracle import raft_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def epe(a, b):
+    return (a - b).pow(2).sum(1).sqrt().mean().item()
+
+
+def split(t):
+    hi = t.half()
+    return hi, (t - hi.float()).half()
+
+
+@pytest.fixture(scope="module")
+def ueng():
+    from rnc.engine_umma import UmmaEngine
+    return UmmaEngine()
+
+
+def test_split_roundtrip_is_near_exact():
+    from rnc import native
+    import ctypes as C
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn(1000, 36, generator=g) * torch.logspace(-4, 3, 36)).to(DEV)
+    hi = torch.zeros(1000, 40, dtype=torch.float16, device=DEV)
+    lo = torch.zeros_like(hi)
+    L = native.lib()
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    native.check(L.rnc_f32_to_split(C.c_void_p(x.data_ptr()), 36, 36, 1000, C.c_void_p(hi.data_ptr()), C.c_void_p(lo.data_ptr()), 40, 2, s))
+    rec = hi[:, 2:38].float() + lo[:, 2:38].float()
+    err = (rec - x).abs()
+    assert (err <= x.abs() * 2.0 ** -21 + 6e-8).all()                   # 22 significant bits, absolute floor = half subnormal
+    assert hi[:, :2].abs().max() == 0 and hi[:, 38:].abs().max() == 0
+
+
+@pytest.mark.parametrize("cin,cout,kh,kw,act,W", [
+    (324, 256, 1, 1, "relu", 21), (256, 192, 3, 3, "relu", 21), (128, 64, 3, 3, "relu", 32), (384, 256, 1, 5, "sigmoid", 21),
+    (384, 128, 5, 1, "none", 64), (132, 64, 3, 3, "relu", 21), (64, 32, 3, 3, "relu", 128), (256, 576, 1, 1, "none", 21)])
+def test_umma_conv_matches_fp32(ueng, cin, cout, kh, kw, act, W):
+    from rnc import native
+    from rnc.engine_umma import SplitBuf, UmmaWeights
+    g = torch.Generator().manual_seed(cin + cout + W)
+    B, H = 2, 13
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, kh, kw, generator=g) / (cin * kh * kw) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=(kh // 2, kw // 2)).float()
+    ref = {"relu": F.relu, "sigmoid": torch.sigmoid, "none": lambda t: t}[act](ref)
+    ld = (cin + 7) // 8 * 8
+    buf = SplitBuf(B * H * W, ld, DEV)
+    x_cl = x.permute(0, 2, 3, 1).reshape(-1, cin).to(DEV)
+    hi, lo = split(x_cl)
+    buf.hi[:, :cin], buf.lo[:, :cin] = hi, lo
+    wt = UmmaWeights(w.to(DEV), b.to(DEV), [cin])
+    out = torch.zeros(B * H * W, wt.coutpad, device=DEV)
+    epi = {"relu": native.EPI_RELU, "sigmoid": native.EPI_SIGMOID, "none": native.EPI_LINEAR}[act]
+    ueng.uconv(B, H, W, buf.ptrs(), cin, ld, wt, epi, out_f32=out.data_ptr(), ldo_f32=wt.coutpad)
+    torch.cuda.synchronize()
+    got = out[:, :cout].view(B, H, W, cout).permute(0, 3, 1, 2).cpu()
+    err = (got - ref).abs().max().item()
+    scale = max(1.0, ref.abs().max().item())
+    print(f"umma conv {cin}->{cout} {kh}x{kw}: max err {err:.2e} (scale {scale:.2f})")
+    assert err < 2e-5 * scale                                             # fp32-class accuracy (TF32 would be ~1e-3)
+    # split output of the same conv reproduces the fp32 output
+    obuf = SplitBuf(B * H * W, wt.coutpad, DEV)
+    ueng.uconv(B, H, W, buf.ptrs(), cin, ld, wt, epi, out_split=obuf.ptrs(), ldo_split=wt.coutpad)
+    rec = (obuf.hi.float() + obuf.lo.float())[:, :cout]
+    assert (rec - out[:, :cout]).abs().max().item() < 1e-6 * scale + 1e-7
+
+
+def test_umma_two_segment_input(ueng):
+    # q-gate convolution: input = cat(r*h [128], x [256]) read from two buffers (update.py:49)
+    from rnc import native
+    from rnc.engine_umma import SplitBuf, UmmaWeights
+    g = torch.Generator().manual_seed(3)
+    B, H, W = 1, 16, 32
+    a, x = torch.randn(B, 128, H, W, generator=g), torch.randn(B, 256, H, W, generator=g)
+    w = torch.randn(128, 384, 1, 5, generator=g) / 44.0
+    b = torch.randn(128, generator=g)
+    ref = F.conv2d(torch.cat([a, x], 1).double(), w.double(), b.double(), padding=(0, 2)).float()
+    sa, sx = SplitBuf(B * H * W, 128, DEV), SplitBuf(B * H * W, 384, DEV)
+    sa.hi[:], sa.lo[:] = split(a.permute(0, 2, 3, 1).reshape(-1, 128).to(DEV))
+    hx, lx = split(x.permute(0, 2, 3, 1).reshape(-1, 256).to(DEV))
+    sx.hi[:, 128:], sx.lo[:, 128:] = hx, lx
+    wt = UmmaWeights(w.to(DEV), b.to(DEV), [128, 256])
+    out = torch.zeros(B * H * W, 128, device=DEV)
+    ueng.uconv(B, H, W, sa.ptrs(), 128, 128, wt, native.EPI_LINEAR, in1=sx.ptrs(128), c1=256, ld1=384, out_f32=out.data_ptr(), ldo_f32=128)
+    got = out.view(B, H, W, 128).permute(0, 3, 1, 2).cpu()
+    assert (got - ref).abs().max() < 2e-5 * ref.abs().max()
+
+
+@pytest.mark.parametrize("it", [0, 3])
+def test_update_block_teacher_forced_umma(gold, it, monkeypatch):
+    monkeypatch.setenv("RNC_CONV", "umma")
+    m = build_model("raft_nc_dbl").to(DEV)
+    flow = gold[f"coords_it{it}"] - orc.coords_grid(1, 16, 32)
+    with torch.no_grad():
+        net, mask, delta = m.update_block(gold[f"net_in_it{it}"].to(DEV), gold["inp"].to(DEV), gold[f"corr_it{it}"].to(DEV), flow.to(DEV))
+    e_net = (net.cpu() - gold[f"net_out_it{it}"]).abs().max().item()
+    e_del = (delta.cpu() - gold[f"delta_it{it}"]).abs().max().item()
+    print(f"umma update block it{it}: net err {e_net:.2e}, delta err {e_del:.2e}")
+    assert e_net < 5e-5 and e_del < 5e-5                                  # same bar as the exact-fp32 path
+
+
+@pytest.mark.parametrize("mode", ["umma", "ffma"])
+@pytest.mark.parametrize("name", ["raft_nc_dbl", "raft"])
+def test_end_to_end_cfg1_both_engines(gold, name, mode, monkeypatch):
+    monkeypatch.setenv("RNC_CONV", mode)
+    m = build_model(name).to(DEV)
+    assert m.engine().mode == mode
+    im1, im2 = frames(1, 128, 256)
+    with torch.no_grad():
+        lo, up = m(im1.to(DEV), im2.to(DEV), iters=4, test_mode=True)
+    e = epe(up.cpu(), gold[f"{name}_flow_up"])
+    print(f"{name}/{mode}: EPE vs reference golden {e:.3e}")
+    assert e < 1e-3 and epe(lo.cpu(), gold[f"{name}_flow_low"]) < 1e-4
+
+
+@pytest.mark.parametrize("mode", ["umma", "ffma"])
+def test_sintel_shape_32_iters_both_engines(mode, monkeypatch):
+    """1024x436 (pad 440), 32 iterations, B=1 vs the CPU oracle for each convolution engine; the two engines must also
+    agree with each other far below the 1e-3 budget."""
+    from utils.utils import InputPadder
+    monkeypatch.setenv("RNC_CONV", mode)
+    m = build_model("raft_nc_dbl").to(DEV)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    im1, im2 = frames(1, 436, 1024)
+    p1, p2 = InputPadder(im1.shape, "sintel").pad(im1, im2)
+    with torch.no_grad():
+        lo, up = m(p1.to(DEV), p2.to(DEV), iters=32, test_mode=True)
+    olo, oup, _ = orc.raft_forward(sd, p1, p2, iters=32, model="raft_nc_dbl", upsample_every_iter=False)
+    e = epe(up.cpu(), oup)
+    print(f"{mode}: EPE flow_up vs oracle {e:.3e} (|flow_up| {oup.abs().mean():.2f})")
+    assert e < 1e-3
