@@ -75,6 +75,22 @@ int rnc_corr_lookup_split_fwd(const float* f1_cl, const float* f2_pyr, const flo
                               int B, int D, int H, int W, int levels, int radius,
                               void* out_hi, void* out_lo, int ldo, void* stream);
 
+/* Tensor-core version of the lookup (tcgen05 + TMA; same reference code, corr.py:7-55 + utils.py:59-73).
+ *   f1h_cl / f2h_pyr : the CL feature map / pyramid of rnc_fmap_prepare rounded once to halves (rnc_f32_to_f16), same
+ *                      element offsets (rnc_pyramid_offset)
+ *   f1_cl / f2_pyr   : the fp32 originals, used by the exact CUDA-core kernel for tiles whose lookup windows do not
+ *                      fit the fixed per-level boxes (incoherent flow) — results never depend on a coherence assumption
+ *   out_hi / out_lo  : CL split halves planes [B][H][W][ldo] (value = hi + lo)
+ *   workspace        : rnc_corr_lookup_umma_workspace_bytes(B,H,W) bytes of device memory (per-tile fallback flags)
+ * Supported: D == 256, levels == 4, radius == 4.
+ */
+size_t rnc_corr_lookup_umma_workspace_bytes(int B, int H, int W);
+int rnc_corr_lookup_umma_fwd(const void* f1h_cl, const void* f2h_pyr, const float* f1_cl, const float* f2_pyr,
+                             const float* coords, int B, int D, int H, int W, int levels, int radius,
+                             void* out_hi, void* out_lo, int ldo, void* workspace, size_t workspace_bytes, void* stream);
+/* fp32 -> fp16 (round to nearest), n % 4 == 0. */
+int rnc_f32_to_f16(const float* src, void* dst, size_t n, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * A5..A8  update block convolutions  (core/update.py:6-14, 33-60, 79-97, 114-141)
  * One generic channel-last convolution with the update block's fusions expressed as epilogues.

@@ -12,9 +12,7 @@
 // GEMM view: M = 128 pixels (a TH x TW patch of one image), N = Cout tile, K = taps x channels in blocks of 64.
 // Zero padding comes for free: the A tile of filter tap (dy,dx) is a 4-D TMA box at (c, x0+dx, y0+dy, b) and
 // out-of-image elements are zero-filled by the TMA unit.
-#include <cuda.h>
-#include <cuda_fp16.h>
-#include "rnc_common.cuh"
+#include "umma_ptx.cuh"
 
 namespace rnc {
 namespace umma {
@@ -37,80 +35,6 @@ struct Params {
   float* h; int ldh;
   float* aux0; int ldaux;
 };
-
-// ---------------------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n.reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n}\n"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must trap, never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], fp16 operands, fp32 accumulate
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, sm100).
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);   // start address   bits [0,14)
-  d |= static_cast<uint64_t>(1) << 16;                   // LBO (unused with swizzle) bits [16,30)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;           // SBO = 1024 B      bits [32,46)
-  d |= static_cast<uint64_t>(1) << 46;                   // descriptor version 1 (Blackwell)
-  d |= static_cast<uint64_t>(2) << 61;                   // SWIZZLE_128B
-  return d;
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // exact hi/lo split of 8 floats into two 16-byte vectors of halves
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
@@ -246,9 +170,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
             dst[q] = make_float4(sigmoidf_(v[4 * q]), sigmoidf_(v[4 * q + 1]), sigmoidf_(v[4 * q + 2]), sigmoidf_(v[4 * q + 3]));
         } else {                 // r gate -> r*h as split halves
           const float4* hp = reinterpret_cast<const float4*>(p.h + pix * p.ldh + (n - Ch));
+          float4 hreg[8];        // all loads first (h is read-only in this kernel): no load->store serialisation
+#pragma unroll
+          for (int q = 0; q < 8; ++q) hreg[q] = __ldg(hp + q);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 hv = hp[q];
+            const float4 hv = hreg[q];
             v[4 * q + 0] = sigmoidf_(v[4 * q + 0]) * hv.x; v[4 * q + 1] = sigmoidf_(v[4 * q + 1]) * hv.y;
             v[4 * q + 2] = sigmoidf_(v[4 * q + 2]) * hv.z; v[4 * q + 3] = sigmoidf_(v[4 * q + 3]) * hv.w;
           }
@@ -262,9 +189,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
       if (epi == RNC_EPI_GRU_Q) {
         const float4* zp = reinterpret_cast<const float4*>(p.aux0 + pix * p.ldaux + n);
         float4* hp = reinterpret_cast<float4*>(p.h + pix * p.ldh + n);
+        float4 zreg[8], hreg[8];   // issue every load before the first store (hp is read-modify-write)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { zreg[q] = __ldg(zp + q); hreg[q] = hp[q]; }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float4 z = zp[q], hv = hp[q];
+          const float4 z = zreg[q], hv = hreg[q];
           v[4 * q + 0] = (1.f - z.x) * hv.x + z.x * tanhf(v[4 * q + 0]);
           v[4 * q + 1] = (1.f - z.y) * hv.y + z.y * tanhf(v[4 * q + 1]);
           v[4 * q + 2] = (1.f - z.z) * hv.z + z.z * tanhf(v[4 * q + 2]);
@@ -313,36 +243,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(f);
-  }
-  return fn;
-}
-
-// activation plane [B][H][W][ld] halves, channels [0,C): 4-D map {C, W, H, B}, box {64, TW, TH, 1}, 128B swizzle, zero fill
-static bool make_act_map(CUtensorMap* m, const void* base, int C, int ld, int B, int H, int W, int TW, int TH) {
-  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  const cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)TW, (cuuint32_t)TH, 1};
-  const cuuint32_t es[4] = {1, 1, 1, 1};
-  return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
 // weight plane [CoutPad][Ktot] halves: 2-D map {Ktot, CoutPad}, box {64, BN}
 static bool make_w_map(CUtensorMap* m, const void* base, int ktot, int coutpad, int bn) {
   const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)coutpad};
   const cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)bn};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)bn};
   const cuuint32_t es[2] = {1, 1};
   return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

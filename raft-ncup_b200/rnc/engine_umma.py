@@ -139,6 +139,14 @@ class UmmaWorkspace:
 class UmmaEngine(Engine):
     mode = "umma"
 
+    def __init__(self):
+        super().__init__()
+        import os
+        # RNC_LOOKUP=umma (default): tcgen05 lookup on fp16 features; RNC_LOOKUP=ffma: exact fp32 CUDA-core lookup
+        self.lookup_mode = os.environ.get("RNC_LOOKUP", "umma").lower()
+        if self.lookup_mode not in ("umma", "ffma"):
+            raise ValueError(f"RNC_LOOKUP={self.lookup_mode!r}: expected 'umma' or 'ffma'")
+
     def packed_update(self, ub):
         from .engine import _param_key
         key = _param_key(ub)
@@ -177,8 +185,30 @@ class UmmaEngine(Engine):
         d.cout, d.kh, d.kw, d.epilogue = wt.cout, wt.kh, wt.kw, epi
         native.check(self.L.rnc_conv2d_umma_fwd(C.byref(d), _stream()), "conv2d_umma")
 
+    def fmap_prepare(self, ws, fmap1, fmap2, levels=4):
+        super().fmap_prepare(ws, fmap1, fmap2, levels)
+        if self.lookup_mode != "umma":
+            return
+        # halves copies of the CL feature map / pyramid: the tensor-core lookup's operands
+        n1, n2 = ws.f1_cl.numel(), ws.f2_pyr.numel()
+        if getattr(ws, "f1h", None) is None or ws.f1h.numel() != n1:
+            ws.f1h = torch.empty(n1, dtype=torch.float16, device=fmap1.device)
+            ws.f2h = torch.empty(n2, dtype=torch.float16, device=fmap1.device)
+            nbytes = self.L.rnc_corr_lookup_umma_workspace_bytes(ws.B, ws.H8, ws.W8)
+            ws.lookup_flags = torch.zeros(nbytes // 4, dtype=torch.int32, device=fmap1.device)
+        s = _stream()
+        native.check(self.L.rnc_f32_to_f16(_ptr(ws.f1_cl), _ptr(ws.f1h), n1, s), "f32_to_f16(f1)")
+        native.check(self.L.rnc_f32_to_f16(_ptr(ws.f2_pyr), _ptr(ws.f2h), n2, s), "f32_to_f16(f2)")
+
     def lookup_resident(self, ws):
         """corr lookup straight into the split planes convc1 consumes."""
+        if self.lookup_mode == "umma":
+            with _Timed(self, "corr_lookup"):
+                native.check(self.L.rnc_corr_lookup_umma_fwd(
+                    _ptr(ws.f1h), _ptr(ws.f2h), _ptr(ws.f1_cl), _ptr(ws.f2_pyr), _ptr(ws.coords1), ws.B, ws.D, ws.H8, ws.W8,
+                    ws.levels, 4, _ptr(ws.corr.hi), _ptr(ws.corr.lo), CORR_LD, _ptr(ws.lookup_flags),
+                    ws.lookup_flags.numel() * 4, _stream()), "corr_lookup_umma")
+            return
         with _Timed(self, "corr_lookup"):
             native.check(self.L.rnc_corr_lookup_split_fwd(_ptr(ws.f1_cl), _ptr(ws.f2_pyr), _ptr(ws.coords1), ws.B, ws.D, ws.H8,
                                                           ws.W8, ws.levels, 4, _ptr(ws.corr.hi), _ptr(ws.corr.lo), CORR_LD,

@@ -63,6 +63,9 @@ SIGNATURES = {
     "rnc_fmap_prepare": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rnc_corr_lookup_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "rnc_corr_lookup_split_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "rnc_corr_lookup_umma_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
+    "rnc_corr_lookup_umma_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, C.c_size_t, _vp]),
+    "rnc_f32_to_f16": (_i, [_vp, _vp, C.c_size_t, _vp]),
     "rnc_conv2d_cl_fwd": (_i, [C.POINTER(ConvDesc), _vp]),
     "rnc_conv2d_umma_fwd": (_i, [C.POINTER(UmmaConvDesc), _vp]),
     "rnc_f32_to_split": (_i, [_vp, _i, _i, C.c_longlong, _vp, _vp, _i, _i, _vp]),

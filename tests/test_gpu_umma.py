@@ -141,3 +141,72 @@ def test_sintel_shape_32_iters_both_engines(mode, monkeypatch):
     e = epe(up.cpu(), oup)
     print(f"{mode}: EPE flow_up vs oracle {e:.3e} (|flow_up| {oup.abs().mean():.2f})")
     assert e < 1e-3
+
+
+# ----------------------------------------------------------------------------- tensor-core correlation lookup
+
+
+def resident_lookup(f1, f2, coords, lookup_mode):
+    """Run the engine's per-iteration lookup into the resident split planes; returns ([B,324,H,W] fp32, flags)."""
+    from rnc.engine_umma import CORR_LD, UmmaEngine
+    eng = UmmaEngine()
+    eng.lookup_mode = lookup_mode
+    B, D, H, W = f1.shape
+    ws = eng.workspace(DEV, B, H, W, False, False)
+    eng.fmap_prepare(ws, f1.to(DEV).contiguous(), f2.to(DEV).contiguous(), 4)
+    ws.coords1.copy_(coords.to(DEV))
+    ws.corr.hi.fill_(7.0)
+    ws.corr.lo.fill_(0.0)
+    eng.lookup_resident(ws)
+    torch.cuda.synchronize()
+    out = (ws.corr.hi.float() + ws.corr.lo.float())
+    assert (ws.corr.hi[:, 324:] == 7.0).all()
+    flags = ws.lookup_flags.cpu() if lookup_mode == "umma" else None
+    return out[:, :324].view(B, H, W, 324).permute(0, 3, 1, 2).cpu(), flags
+
+
+def fp16_tol(f1, f2):
+    # |err| of a 256-term dot product of fp16-rounded operands / 16: ~ sqrt(256) * |f1||f2| * 2^-11 * sqrt(2) / 16
+    return 6.0 * (256 ** 0.5) * f1.abs().max().item() * f2.abs().max().item() * 2.0 ** -11 / 16 / 4
+
+
+@pytest.mark.parametrize("it", [0, 3])
+def test_umma_lookup_matches_reference_golden(gold, it):
+    out, flags = resident_lookup(gold["fmap1"], gold["fmap2"], gold[f"coords_it{it}"], "umma")
+    ref = gold[f"corr_it{it}"]
+    err = (out - ref).abs()
+    print(f"umma lookup it{it}: max err {err.max():.2e} mean {err.mean():.2e} (|ref| max {ref.abs().max():.1f}), fallback tiles {int(flags.sum())}")
+    assert flags.sum() == 0
+    assert err.max() < fp16_tol(gold["fmap1"], gold["fmap2"]) and err.mean() < 1e-3
+    exact, _ = resident_lookup(gold["fmap1"], gold["fmap2"], gold[f"coords_it{it}"], "ffma")
+    assert (exact - ref).abs().max() < 1e-4
+
+
+def test_umma_lookup_full_size_borders_and_fallback():
+    g = torch.Generator().manual_seed(33)
+    B, H, W = 2, 55, 128
+    f1 = torch.randn(B, 256, H, W, generator=g) * 1.5
+    f2 = torch.randn(B, 256, H, W, generator=g) * 1.5
+    # smooth flow (coherent tiles) pushed across the image borders + one incoherent region -> fallback tiles
+    yy, xx = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing="ij")
+    flow = torch.stack([6 * torch.sin(yy / 9) + 0.03 * xx - 3.3, 5 * torch.cos(xx / 17) - 0.05 * yy + 2.7], 0)[None].repeat(B, 1, 1, 1)
+    flow[1, :, 20:30, 40:70] += torch.randn(2, 10, 30, generator=g) * 12
+    flow[0, :, 0, 0] = torch.tensor([1e9, -1e9])
+    co = orc.coords_grid(B, H, W) + flow
+    out, flags = resident_lookup(f1, f2, co, "umma")
+    exact, _ = resident_lookup(f1, f2, co, "ffma")
+    nf = int(flags.sum())
+    err = (out - exact).abs()
+    print(f"umma lookup 55x128: max err {err.max():.2e} mean {err.mean():.2e}, fallback tiles {nf}/{flags.numel()}")
+    assert 0 < nf < flags.numel() // 2
+    assert err.max() < fp16_tol(f1, f2) and err.mean() < 1e-3
+    # spot check the exact path itself against the oracle on one image
+    ref = orc.corr_lookup_direct(f1[:1], f2[:1], co[:1].clamp(-1e6, 1e6))
+    assert (exact[:1] - ref).abs().max() < 2e-4
+
+
+def test_umma_lookup_odd_size(gold):
+    out, flags = resident_lookup(gold["odd_f1"], gold["odd_f2"], gold["odd_coords"], "umma")
+    err = (out - gold["odd_corr"]).abs()
+    print(f"umma lookup 17x21 randn*6: max err {err.max():.2e}, fallback tiles {int(flags.sum())}/{flags.numel()}")
+    assert err.max() < fp16_tol(gold["odd_f1"], gold["odd_f2"])
