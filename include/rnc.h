@@ -104,9 +104,15 @@ typedef enum {
   RNC_EPI_GRU_ZR = 3,   /* Cout = 2*C: ch<C: aux0[p][ch] = z = sigmoid(.)                       */
                         /*             ch>=C: out[p][ch-C] = sigmoid(.) * h[p][ch-C]   update.py:47-49 */
   RNC_EPI_GRU_Q = 4,    /* q = tanh(.); h[p][ch] = (1-z)*h + z*q with z = aux0       update.py:49-50 */
-  RNC_EPI_RELU_FLOW = 5 /* RELU, and channels [Cout, Cout+2) of out receive flow = coords1-coords0 (update.py:97);
+  RNC_EPI_RELU_FLOW = 5,/* RELU, and channels [Cout, Cout+2) of out receive flow = coords1-coords0 (update.py:97);
                            aux0 = coords1 NCHW [B][2][H][W]                                     */
+  RNC_EPI_RELU_ADD_RELU = 6, /* relu(res + relu(acc + bias)): residual block tail, extractor.py:48-55 (umma only) */
+  RNC_EPI_TANH_RELU = 7      /* ch < Cout/2: tanh (-> out_f32 and split), else relu (-> split): raft_nc_dbl.py:138-140 (umma only) */
 } rnc_epilogue;
+
+/* rnc_conv_umma_desc.flags */
+#define RNC_CONV_NO_HALO 1          /* force one A tile per filter tap (disable the row/column halo sharing) */
+#define RNC_CONV_BASE_OFFSET 2      /* debug: set the descriptor base_offset for row-shifted taps (wrong on B200) */
 
 typedef struct {
   const float* in0; int c0; int ld0;   /* segment 0: channels [0,c0), pixel stride ld0 floats   */
@@ -146,6 +152,10 @@ typedef struct {
   int cout;
   int kh, kw;
   int epilogue;
+  int stride;                          /* 1 (or 0) | 2: output pixel (y,x) reads input (stride*y + ky - kh/2, ...) */
+  int hin, win;                        /* input height/width (0 -> same as H, W)                                    */
+  const float* res; int ldres;         /* residual (fp32 CL at output resolution) for RELU_ADD_RELU                 */
+  int flags;                           /* RNC_CONV_*                                                                 */
 } rnc_conv_umma_desc;
 
 int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream);

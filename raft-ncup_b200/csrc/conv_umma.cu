@@ -1,32 +1,38 @@
-// tcgen05 implicit-GEMM convolution for the update block (v2 of conv_ffma.cu): A and B tiles staged by TMA into
-// 128B-swizzled shared memory, tcgen05.mma (kind::f16, M128 x N<=256 x K16) issued by one thread, fp32 accumulators in
-// TMEM, epilogue warps read them back with tcgen05.ld and apply the update block's fusions.
-// Replaces the same reference code as conv_ffma.cu: core/update.py:33-60, 79-97, 6-14, 123-126 and the 3x3 layers of
-// core/interp_weights_est.py:10-47.
+// tcgen05 implicit-GEMM convolution (v3): persistent CTAs, TMA-staged 128B-swizzled operand rings, tcgen05.mma
+// (kind::f16, M128 x N<=256 x K16) issued by one thread, fp32 accumulators double-buffered in TMEM so that the epilogue
+// of tile i overlaps the main loop of tile i+1.
+// Replaces: core/update.py:33-60 (SepConvGRU), :79-97 (BasicMotionEncoder), :6-14 (FlowHead), :123-126 (mask head), the 3x3
+// layers of core/interp_weights_est.py:10-47 and (stride 1/2, residual epilogue) the convolutions of
+// core/extractor.py:6-56,118-192.
 //
-// fp32-faithful on fp16 tensor cores: every activation x and weight w is carried as an exact-sum pair of halves
-// (x = x_hi + x_lo, |x_lo| <= ulp(x_hi)/2; weights pre-scaled by a power of two so w_lo stays normal) and the product is
-// accumulated as  x_hi*w_hi + x_hi*w_lo + x_lo*w_hi  — 3 MMAs per K step, relative error ~2^-21 per term, which keeps the
-// 32-iteration recurrence inside the 1e-3 EPE budget where plain TF32/bf16 operands do not.
+// fp32-faithful on fp16 tensor cores: every activation x and weight w is an exact-sum pair of halves (x = x_hi + x_lo;
+// weights pre-scaled by a power of two so w_lo stays normal) and each K step issues x_hi*w_hi + x_hi*w_lo + x_lo*w_hi
+// (3 MMAs): plain TF32/bf16 operands miss the 1e-3 EPE bar by 17-60x.
 //
-// GEMM view: M = 128 pixels (a TH x TW patch of one image), N = Cout tile, K = taps x channels in blocks of 64.
-// Zero padding comes for free: the A tile of filter tap (dy,dx) is a 4-D TMA box at (c, x0+dx, y0+dy, b) and
-// out-of-image elements are zero-filled by the TMA unit.
+// GEMM view: M = 128 output pixels, N = Cout tile, K = taps x 64-channel blocks.  Zero padding is free: A tiles are
+// 4-D TMA boxes whose out-of-image elements are zero-filled.  Three A-staging modes cut the L2->SM traffic of the taps:
+//   TAP      one 128-row box per filter tap (any geometry, strides 1 and 2 via TMA element strides)
+//   ROWHALO  tile = 1 image row x 128 px: one (128 + 8)-row box per (ky, channel block); the kw horizontal taps are
+//            operand descriptors shifted by kx rows (descriptor base_offset carries the swizzle phase)
+//   COLHALO  kw == 1: tile = 8 x 16 px with a vertical halo, the kh taps are descriptors shifted by ky*16 rows
 #include "umma_ptx.cuh"
 
 namespace rnc {
 namespace umma {
 
 constexpr int kThreads = 192;        // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
-constexpr int kBM = 128;             // pixels per tile
-constexpr int kBK = 64;              // channels per stage (64 halves = one 128-byte swizzle row)
-constexpr int kATile = kBM * kBK * 2;   // 16 KB per half-plane
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kMaxSA = 4, kMaxSB = 8;
+enum { MODE_TAP = 0, MODE_ROWHALO = 1, MODE_COLHALO = 2 };
 
 struct Params {
-  // tile geometry
-  int B, H, W, TW, TH, tiles_x, tiles_y;
-  int kw, ph, pw, ntaps;
-  int nblk0, nblk;                   // 64-channel blocks in segment 0 / in total (per tap)
+  int B, H, W;                        // output geometry
+  int TW, TH, tiles_x, tiles_y, ntiles, ntn;
+  int mode, kh, kw, ph, pw, stride;
+  int nblk0, nblk;                    // 64-channel blocks in segment 0 / total
+  int a_plane, SA, SB;                // bytes per A half-plane stage (rows*128, 1024-aligned), ring depths
+  int use_base_offset;
   int cout, epilogue;
   float unscale;
   const float* bias;
@@ -34,7 +40,13 @@ struct Params {
   __half* out_hi; __half* out_lo; int ldo_split;
   float* h; int ldh;
   float* aux0; int ldaux;
+  const float* res; int ldres;
 };
+
+// K-major SW128 descriptor with a row shift inside the 8-row swizzle atom (base_offset = (addr >> 7) & 7)
+__device__ __forceinline__ uint64_t smem_desc_sw128_shift(uint32_t saddr) {
+  return smem_desc_sw128(saddr) | (static_cast<uint64_t>((saddr >> 7) & 7u) << 49);
+}
 
 // exact hi/lo split of 8 floats into two 16-byte vectors of halves
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
@@ -53,10 +65,7 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
 template <int BN>
 struct Cfg {
   static constexpr int kBTile = BN * kBK * 2;                     // bytes per half-plane of weights
-  static constexpr int kStage = 2 * kATile + 2 * kBTile;
-  static constexpr int kStages = (200 * 1024) / kStage > 4 ? 4 : (200 * 1024) / kStage;
-  static constexpr int kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-  static constexpr int kSmem = kStages * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = BN <= 32 ? 64 : BN <= 64 ? 128 : BN <= 128 ? 256 : 512;   // two accumulators
 };
 
 template <int BN>
@@ -67,28 +76,31 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
   using C = Cfg<BN>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStage);
-  uint64_t* empty = full + C::kStages;
-  uint64_t* tmem_full = empty + C::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  const int a_stage = 2 * p.a_plane;
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + p.SA * a_stage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.SB * 2 * C::kBTile);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kMaxSA;
+  uint64_t* b_full = a_empty + kMaxSA;
+  uint64_t* b_empty = b_full + kMaxSB;
+  uint64_t* acc_full = b_empty + kMaxSB;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
+  const int items = p.ntiles * p.ntn;
   const int tpi = p.tiles_x * p.tiles_y;
-  const int b = tile / tpi, tr = tile - b * tpi;
-  const int y0 = (tr / p.tiles_x) * p.TH, x0 = (tr % p.tiles_x) * p.TW;
-  const int n0 = blockIdx.y * BN;
-  const int nk = p.ntaps * p.nblk;
+  const int G = p.mode == MODE_TAP ? p.kh * p.kw : p.mode == MODE_ROWHALO ? p.kh : 1;     // A-stage groups per channel block
+  const int T = p.mode == MODE_TAP ? 1 : p.mode == MODE_ROWHALO ? p.kw : p.kh;            // taps sharing one A stage
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int s = 0; s < p.SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < p.SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -97,139 +109,210 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      for (int it = 0; it < nk; ++it) {
-        const int s = it % C::kStages, ph = (it / C::kStages) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        unsigned char* st = smem + s * C::kStage;
-        mbar_expect_tx(&full[s], C::kStage);
-        const int tap = it / p.nblk, cb = it - tap * p.nblk;
-        const int dy = tap / p.kw - p.ph, dx = tap % p.kw - p.pw;
-        const bool seg0 = cb < p.nblk0;
-        const int c = (seg0 ? cb : cb - p.nblk0) * kBK;
-        tma_load_4d(st, seg0 ? &mA0h : &mA1h, &full[s], c, x0 + dx, y0 + dy, b);
-        tma_load_4d(st + kATile, seg0 ? &mA0l : &mA1l, &full[s], c, x0 + dx, y0 + dy, b);
-        tma_load_2d(st + 2 * kATile, &mBh, &full[s], it * kBK, n0);
-        tma_load_2d(st + 2 * kATile + C::kBTile, &mBl, &full[s], it * kBK, n0);
+      int a_it = 0, b_it = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int tile = item / p.ntn, n0 = (item - tile * p.ntn) * BN;
+        const int b = tile / tpi, tr = tile - b * tpi;
+        const int y0 = (tr / p.tiles_x) * p.TH, x0 = (tr % p.tiles_x) * p.TW;
+        for (int g = 0; g < G; ++g) {
+          int cx, cy;
+          if (p.mode == MODE_TAP) { cx = x0 * p.stride + g % p.kw - p.pw; cy = y0 * p.stride + g / p.kw - p.ph; }
+          else if (p.mode == MODE_ROWHALO) { cx = x0 - p.pw; cy = y0 + g - p.ph; }
+          else { cx = x0; cy = y0 - p.ph; }
+          for (int cb = 0; cb < p.nblk; ++cb) {
+            const int sa = a_it % p.SA, pa = (a_it / p.SA) & 1;
+            ++a_it;
+            mbar_wait(&a_empty[sa], pa ^ 1);
+            mbar_expect_tx(&a_full[sa], a_stage);
+            const bool seg0 = cb < p.nblk0;
+            const int c = (seg0 ? cb : cb - p.nblk0) * kBK;
+            tma_load_4d(sA + sa * a_stage, seg0 ? &mA0h : &mA1h, &a_full[sa], c, cx, cy, b);
+            tma_load_4d(sA + sa * a_stage + p.a_plane, seg0 ? &mA0l : &mA1l, &a_full[sa], c, cx, cy, b);
+            for (int t = 0; t < T; ++t) {
+              const int tap = p.mode == MODE_TAP ? g : p.mode == MODE_ROWHALO ? g * p.kw + t : t;
+              const int sb = b_it % p.SB, pb = (b_it / p.SB) & 1;
+              ++b_it;
+              mbar_wait(&b_empty[sb], pb ^ 1);
+              mbar_expect_tx(&b_full[sb], 2 * C::kBTile);
+              const int kcol = (tap * p.nblk + cb) * kBK;
+              tma_load_2d(sB + sb * 2 * C::kBTile, &mBh, &b_full[sb], kcol, n0);
+              tma_load_2d(sB + sb * 2 * C::kBTile + C::kBTile, &mBl, &b_full[sb], kcol, n0);
+            }
+          }
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (single thread)
     if (lane == 0) {
-      // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6), A=B=F16, K-major, N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(kBM >> 4) << 24);
-      for (int it = 0; it < nk; ++it) {
-        const int s = it % C::kStages, ph = (it / C::kStages) & 1;
-        mbar_wait(&full[s], ph);
+      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+      const int shift_rows = p.mode == MODE_ROWHALO ? 1 : p.mode == MODE_COLHALO ? p.TW : 0;
+      int a_it = 0, b_it = 0, t_it = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++t_it) {
+        const int buf = t_it & 1, use = t_it >> 1;
+        mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
         tcgen05_fence_after();
-        const uint32_t sa = smem_u32(smem + s * C::kStage);
-        const uint64_t ah = smem_desc_sw128(sa), al = smem_desc_sw128(sa + kATile);
-        const uint64_t bh = smem_desc_sw128(sa + 2 * kATile), bl = smem_desc_sw128(sa + 2 * kATile + C::kBTile);
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        uint32_t acc = 0;
+        for (int g = 0; g < G; ++g)
+          for (int cb = 0; cb < p.nblk; ++cb) {
+            const int sa = a_it % p.SA, pa = (a_it / p.SA) & 1;
+            ++a_it;
+            mbar_wait(&a_full[sa], pa);
+            for (int t = 0; t < T; ++t) {
+              const int sb = b_it % p.SB, pb = (b_it / p.SB) & 1;
+              ++b_it;
+              mbar_wait(&b_full[sb], pb);
+              tcgen05_fence_after();
+              const uint32_t ar = a_base + sa * a_stage + t * shift_rows * 128;
+              const uint64_t ah = p.use_base_offset ? smem_desc_sw128_shift(ar) : smem_desc_sw128(ar);
+              const uint64_t al = p.use_base_offset ? smem_desc_sw128_shift(ar + p.a_plane) : smem_desc_sw128(ar + p.a_plane);
+              const uint32_t br = b_base + sb * 2 * C::kBTile;
+              const uint64_t bh = smem_desc_sw128(br), bl = smem_desc_sw128(br + C::kBTile);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          const uint64_t ko = static_cast<uint64_t>((k * 32) >> 4);     // advance 16 halves = 32 B inside the swizzle row
-          umma_f16(tmem_base, ah + ko, bh + ko, idesc, (it | k) != 0);
-          umma_f16(tmem_base, ah + ko, bl + ko, idesc, 1);
-          umma_f16(tmem_base, al + ko, bh + ko, idesc, 1);
-        }
-        umma_commit(&empty[s]);          // frees the stage once these MMAs have read it
+              for (int k = 0; k < kBK / 16; ++k) {
+                umma_f16(d_tmem, ah + 2 * k, bh + 2 * k, idesc, acc);
+                acc = 1;
+                umma_f16(d_tmem, ah + 2 * k, bl + 2 * k, idesc, 1);
+                umma_f16(d_tmem, al + 2 * k, bh + 2 * k, idesc, 1);
+              }
+              umma_commit(&b_empty[sb]);
+            }
+            umma_commit(&a_empty[sa]);
+          }
+        umma_commit(&acc_full[buf]);
       }
-      umma_commit(tmem_full);            // accumulator complete
     }
   } else {
     // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
     const int lg = warp & 3;                       // TMEM lane group this warp may access
     const int ml = lg * 32 + lane;                 // row of the tile = pixel
-    const int y = y0 + ml / p.TW, x = x0 + ml % p.TW;
-    const bool valid = y < p.H && x < p.W;
-    const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
-    mbar_wait(tmem_full, 0);
-    tcgen05_fence_after();
     const int epi = p.epilogue;
+    int t_it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++t_it) {
+      const int tile = item / p.ntn, n0 = (item - tile * p.ntn) * BN;
+      const int b = tile / tpi, tr = tile - b * tpi;
+      const int y = (tr / p.tiles_x) * p.TH + ml / p.TW, x = (tr % p.tiles_x) * p.TW + ml % p.TW;
+      const bool valid = y < p.H && x < p.W;
+      const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
+      const int buf = t_it & 1, use = t_it >> 1;
+      mbar_wait(&acc_full[buf], use & 1);
+      tcgen05_fence_after();
 #pragma unroll 1
-    for (int cc = 0; cc < BN / 32; ++cc) {
-      const int n = n0 + cc * 32;
-      if (n >= p.cout + (epi == RNC_EPI_RELU_FLOW ? 2 : 0)) break;   // warp-uniform
-      uint32_t r[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + cc * 32, r);
-      if (!valid) continue;
-      float v[32];
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        const int n = n0 + cc * 32;
+        if (n >= p.cout + (epi == RNC_EPI_RELU_FLOW ? 2 : 0)) break;   // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + buf * BN + cc * 32, r);
+        if (!valid) continue;
+        float v[32];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n) + q);
-        v[4 * q + 0] = fmaf(__uint_as_float(r[4 * q + 0]), p.unscale, bv.x);
-        v[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]), p.unscale, bv.y);
-        v[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]), p.unscale, bv.z);
-        v[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]), p.unscale, bv.w);
-      }
-      if (epi == RNC_EPI_GRU_ZR) {
-        const int Ch = p.cout >> 1;
-        if (n < Ch) {            // z gate -> fp32 aux buffer
-          float4* dst = reinterpret_cast<float4*>(p.aux0 + pix * p.ldaux + n);
+        for (int q = 0; q < 8; ++q) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n) + q);
+          v[4 * q + 0] = fmaf(__uint_as_float(r[4 * q + 0]), p.unscale, bv.x);
+          v[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]), p.unscale, bv.y);
+          v[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]), p.unscale, bv.z);
+          v[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]), p.unscale, bv.w);
+        }
+        if (epi == RNC_EPI_GRU_ZR) {
+          const int Ch = p.cout >> 1;
+          if (n < Ch) {            // z gate -> fp32 aux buffer
+            float4* dst = reinterpret_cast<float4*>(p.aux0 + pix * p.ldaux + n);
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            dst[q] = make_float4(sigmoidf_(v[4 * q]), sigmoidf_(v[4 * q + 1]), sigmoidf_(v[4 * q + 2]), sigmoidf_(v[4 * q + 3]));
-        } else {                 // r gate -> r*h as split halves
-          const float4* hp = reinterpret_cast<const float4*>(p.h + pix * p.ldh + (n - Ch));
-          float4 hreg[8];        // all loads first (h is read-only in this kernel): no load->store serialisation
+            for (int q = 0; q < 8; ++q)
+              dst[q] = make_float4(sigmoidf_(v[4 * q]), sigmoidf_(v[4 * q + 1]), sigmoidf_(v[4 * q + 2]), sigmoidf_(v[4 * q + 3]));
+          } else {                 // r gate -> r*h as split halves
+            const float4* hp = reinterpret_cast<const float4*>(p.h + pix * p.ldh + (n - Ch));
+            float4 hreg[8];        // all loads first (h is read-only here): no load->store serialisation
 #pragma unroll
-          for (int q = 0; q < 8; ++q) hreg[q] = __ldg(hp + q);
+            for (int q = 0; q < 8; ++q) hreg[q] = __ldg(hp + q);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 hv = hreg[q];
+              v[4 * q + 0] = sigmoidf_(v[4 * q + 0]) * hv.x; v[4 * q + 1] = sigmoidf_(v[4 * q + 1]) * hv.y;
+              v[4 * q + 2] = sigmoidf_(v[4 * q + 2]) * hv.z; v[4 * q + 3] = sigmoidf_(v[4 * q + 3]) * hv.w;
+            }
+            uint4* dh = reinterpret_cast<uint4*>(p.out_hi + pix * p.ldo_split + (n - Ch));
+            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + pix * p.ldo_split + (n - Ch));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) split8(v + 8 * q, dh[q], dl[q]);
+          }
+          continue;
+        }
+        bool want_f32 = p.out_f32 != nullptr;
+        if (epi == RNC_EPI_GRU_Q) {
+          const float4* zp = reinterpret_cast<const float4*>(p.aux0 + pix * p.ldaux + n);
+          float4* hp = reinterpret_cast<float4*>(p.h + pix * p.ldh + n);
+          float4 zreg[8], hreg[8];   // issue every load before the first store (hp is read-modify-write)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { zreg[q] = __ldg(zp + q); hreg[q] = hp[q]; }
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 hv = hreg[q];
-            v[4 * q + 0] = sigmoidf_(v[4 * q + 0]) * hv.x; v[4 * q + 1] = sigmoidf_(v[4 * q + 1]) * hv.y;
-            v[4 * q + 2] = sigmoidf_(v[4 * q + 2]) * hv.z; v[4 * q + 3] = sigmoidf_(v[4 * q + 3]) * hv.w;
+            const float4 z = zreg[q], hv = hreg[q];
+            v[4 * q + 0] = (1.f - z.x) * hv.x + z.x * tanhf(v[4 * q + 0]);
+            v[4 * q + 1] = (1.f - z.y) * hv.y + z.y * tanhf(v[4 * q + 1]);
+            v[4 * q + 2] = (1.f - z.z) * hv.z + z.z * tanhf(v[4 * q + 2]);
+            v[4 * q + 3] = (1.f - z.w) * hv.w + z.w * tanhf(v[4 * q + 3]);
+            hp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
-          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + pix * p.ldo_split + (n - Ch));
-          uint4* dl = reinterpret_cast<uint4*>(p.out_lo + pix * p.ldo_split + (n - Ch));
+        } else if (epi == RNC_EPI_RELU || epi == RNC_EPI_RELU_FLOW) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          if (epi == RNC_EPI_RELU_FLOW && n <= p.cout && p.cout < n + 32) {
+            // append flow = coords1 - grid as channels [cout, cout+2)  (update.py:97)
+            const int HW = p.H * p.W;
+            const float* c1 = p.aux0 + static_cast<size_t>(b) * 2 * HW + y * p.W + x;
+            const float fx = c1[0] - static_cast<float>(x), fy = c1[HW] - static_cast<float>(y);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (n + j == p.cout) v[j] = fx;
+              if (n + j == p.cout + 1) v[j] = fy;
+            }
+          }
+        } else if (epi == RNC_EPI_SIGMOID) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = sigmoidf_(v[j]);
+        } else if (epi == RNC_EPI_RELU_ADD_RELU) {
+          // residual block tail (extractor.py:55): relu(x + relu(norm(conv(.)))) with the norm folded into the weights
+          const float4* rp = reinterpret_cast<const float4*>(p.res + pix * p.ldres + n);
+          float4 rreg[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) rreg[q] = __ldg(rp + q);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            v[4 * q + 0] = fmaxf(rreg[q].x + fmaxf(v[4 * q + 0], 0.f), 0.f);
+            v[4 * q + 1] = fmaxf(rreg[q].y + fmaxf(v[4 * q + 1], 0.f), 0.f);
+            v[4 * q + 2] = fmaxf(rreg[q].z + fmaxf(v[4 * q + 2], 0.f), 0.f);
+            v[4 * q + 3] = fmaxf(rreg[q].w + fmaxf(v[4 * q + 3], 0.f), 0.f);
+          }
+        } else if (epi == RNC_EPI_TANH_RELU) {
+          // context encoder head (raft_nc_dbl.py:138-140): first half tanh -> net, second half relu -> inp
+          if (n < (p.cout >> 1)) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            want_f32 = false;
+          }
+        }
+        if (want_f32) {
+          float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.ldo_f32 + n);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        if (p.out_hi) {
+          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + pix * p.ldo_split + n);
+          uint4* dl = reinterpret_cast<uint4*>(p.out_lo + pix * p.ldo_split + n);
 #pragma unroll
           for (int q = 0; q < 4; ++q) split8(v + 8 * q, dh[q], dl[q]);
         }
-        continue;
       }
-      if (epi == RNC_EPI_GRU_Q) {
-        const float4* zp = reinterpret_cast<const float4*>(p.aux0 + pix * p.ldaux + n);
-        float4* hp = reinterpret_cast<float4*>(p.h + pix * p.ldh + n);
-        float4 zreg[8], hreg[8];   // issue every load before the first store (hp is read-modify-write)
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { zreg[q] = __ldg(zp + q); hreg[q] = hp[q]; }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 z = zreg[q], hv = hreg[q];
-          v[4 * q + 0] = (1.f - z.x) * hv.x + z.x * tanhf(v[4 * q + 0]);
-          v[4 * q + 1] = (1.f - z.y) * hv.y + z.y * tanhf(v[4 * q + 1]);
-          v[4 * q + 2] = (1.f - z.z) * hv.z + z.z * tanhf(v[4 * q + 2]);
-          v[4 * q + 3] = (1.f - z.w) * hv.w + z.w * tanhf(v[4 * q + 3]);
-          hp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        }
-      } else if (epi == RNC_EPI_RELU || epi == RNC_EPI_RELU_FLOW) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        if (epi == RNC_EPI_RELU_FLOW && n <= p.cout && p.cout < n + 32) {
-          // append flow = coords1 - grid as channels [cout, cout+2)  (update.py:97)
-          const int HW = p.H * p.W;
-          const float* c1 = p.aux0 + static_cast<size_t>(b) * 2 * HW + y * p.W + x;
-          const float fx = c1[0] - static_cast<float>(x), fy = c1[HW] - static_cast<float>(y);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (n + j == p.cout) v[j] = fx;
-            if (n + j == p.cout + 1) v[j] = fy;
-          }
-        }
-      } else if (epi == RNC_EPI_SIGMOID) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = sigmoidf_(v[j]);
-      }
-      if (p.out_f32) {
-        float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.ldo_f32 + n);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      }
-      if (p.out_hi) {
-        uint4* dh = reinterpret_cast<uint4*>(p.out_hi + pix * p.ldo_split + n);
-        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + pix * p.ldo_split + n);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) split8(v + 8 * q, dh[q], dl[q]);
-      }
+      // this warp has finished reading the accumulator buffer (tcgen05.wait::ld inside tmem_ld32)
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
   }
 
@@ -238,11 +321,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
+    tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
 // ---------------------------------------------------------------------------------------------- host side
+// activation plane [B][Hin][Win][ld] halves: 4-D map {C, Win, Hin, B}; the box spans bw x bh input elements and is
+// traversed with element strides (sx, sy) -> (bw/sx) x (bh/sy) rows of 64 channels in shared memory
+static bool make_in_map(CUtensorMap* m, const void* base, int C, int ld, int B, int Hin, int Win, int bw, int bh, int stride) {
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)Win * ld * 2, (cuuint64_t)Hin * Win * ld * 2};
+  const cuuint32_t box[4] = {64u, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), 1};
+  const cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 // weight plane [CoutPad][Ktot] halves: 2-D map {Ktot, CoutPad}, box {64, BN}
 static bool make_w_map(CUtensorMap* m, const void* base, int ktot, int coutpad, int bn) {
   const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)coutpad};
@@ -254,11 +348,30 @@ static bool make_w_map(CUtensorMap* m, const void* base, int ktot, int coutpad, 
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int BN>
-static int launch(const CUtensorMap* maps, const Params& p, int ntiles, int ngrid_n, cudaStream_t stream) {
+static int launch(const CUtensorMap* maps, Params& p, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  // ring depths: A double buffered, B as deep as fits ~200 KB
+  const int a_stage = 2 * p.a_plane;
+  p.SA = 2;
+  int sb = (200 * 1024 - p.SA * a_stage) / (2 * C::kBTile);
+  p.SB = sb > kMaxSB ? kMaxSB : sb < 2 ? 2 : sb;
+  const int smem = p.SA * a_stage + p.SB * 2 * C::kBTile + 1024 + 512;
   static unsigned long long done = 0;
-  if (int st = ensure_dyn_smem(conv_umma_kernel<BN>, Cfg<BN>::kSmem, &done)) return st;
-  conv_umma_kernel<BN><<<dim3(ntiles, ngrid_n), kThreads, Cfg<BN>::kSmem, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  if (int st = ensure_dyn_smem(conv_umma_kernel<BN>, 227 * 1024, &done)) return st;
+  const int items = p.ntiles * p.ntn;
+  const int grid = items < sm_count() ? items : sm_count();
+  conv_umma_kernel<BN><<<grid, kThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   return after_launch();
 }
 
@@ -271,7 +384,9 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   using namespace rnc::umma;
   if (!desc) return RNC_ERR_BAD_POINTER;
   const rnc_conv_umma_desc& d = *desc;
-  if (d.B <= 0 || d.H <= 0 || d.W <= 0 || d.cout <= 0 || d.c0 <= 0 || d.c1 < 0) return RNC_ERR_BAD_SHAPE;
+  const int stride = d.stride <= 0 ? 1 : d.stride;
+  const int Hin = d.hin > 0 ? d.hin : d.H, Win = d.win > 0 ? d.win : d.W;
+  if (d.B <= 0 || d.H <= 0 || d.W <= 0 || d.cout <= 0 || d.c0 <= 0 || d.c1 < 0 || stride > 2) return RNC_ERR_BAD_SHAPE;
   if (d.kh < 1 || d.kw < 1 || !(d.kh & 1) || !(d.kw & 1) || d.kh * d.kw > 49) return RNC_ERR_BAD_SHAPE;
   if ((d.ld0 & 7) || d.ld0 < d.c0 || (d.c1 > 0 && ((d.c0 % kBK) != 0 || (d.ld1 & 7) || d.ld1 < d.c1))) return RNC_ERR_BAD_SHAPE;
   if (!d.in0_hi || !d.in0_lo || (d.c1 > 0 && (!d.in1_hi || !d.in1_lo)) || !d.w_hi || !d.w_lo || !d.bias) return RNC_ERR_BAD_POINTER;
@@ -280,22 +395,25 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   const int nblk0 = (d.c0 + kBK - 1) / kBK, nblk1 = (d.c1 + kBK - 1) / kBK, nblk = nblk0 + nblk1;
   const int ntaps = d.kh * d.kw;
   if (d.ktot != ntaps * nblk * kBK) return RNC_ERR_BAD_SHAPE;          // weight planes are [coutpad][taps * blocks * 64]
-  // N tile: the whole Cout in one CTA when it fits 256 TMEM columns, else equal tiles
   int bn;
   if (d.coutpad <= 32) bn = 32; else if (d.coutpad <= 64) bn = 64; else if (d.coutpad <= 128) bn = 128;
-  else if (d.coutpad == 192 || d.coutpad % 192 == 0) bn = 192; else bn = 256;
+  else if (d.coutpad % 192 == 0) bn = 192; else bn = 256;
   if (d.coutpad % bn != 0 || d.coutpad < d.cout) return RNC_ERR_BAD_SHAPE;
   if (d.epilogue == RNC_EPI_RELU_FLOW && (d.coutpad < d.cout + 2 || !d.aux0 || !d.out_hi)) return RNC_ERR_BAD_SHAPE;
   if (d.out_hi && (!d.out_lo || (d.ldo_split & 7) || !aligned16(d.out_hi) || !aligned16(d.out_lo))) return RNC_ERR_BAD_POINTER;
   if (d.out_f32 && ((d.ldo_f32 & 3) || !aligned16(d.out_f32))) return RNC_ERR_BAD_POINTER;
   switch (d.epilogue) {
-    case RNC_EPI_LINEAR: case RNC_EPI_RELU: case RNC_EPI_SIGMOID: case RNC_EPI_RELU_FLOW:
+    case RNC_EPI_RELU_ADD_RELU:
+      if (!d.res || (d.ldres & 3) || !aligned16(d.res)) return RNC_ERR_BAD_POINTER;
+      /* fall through */
+    case RNC_EPI_LINEAR: case RNC_EPI_RELU: case RNC_EPI_SIGMOID: case RNC_EPI_RELU_FLOW: case RNC_EPI_TANH_RELU:
       if (!d.out_f32 && !d.out_hi) return RNC_ERR_BAD_POINTER;
       if ((d.cout % 32) != 0 && d.epilogue != RNC_EPI_RELU_FLOW) {
         // the epilogue stores whole 32-channel chunks: the destination must have room for the padded tail
         const int cpad = (d.cout + 31) / 32 * 32;
         if ((d.out_f32 && d.ldo_f32 < cpad) || (d.out_hi && d.ldo_split < cpad)) return RNC_ERR_BAD_SHAPE;
       }
+      if (d.epilogue == RNC_EPI_TANH_RELU && (d.cout % 64) != 0) return RNC_ERR_BAD_SHAPE;
       break;
     case RNC_EPI_GRU_ZR:
       if (!d.out_hi || !d.aux0 || !d.h || (d.cout % 64) != 0 || (d.ldaux & 3) || (d.ldh & 3)) return RNC_ERR_BAD_POINTER;
@@ -307,39 +425,55 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   }
   if (!encode_fn()) return RNC_ERR_UNSUPPORTED;
 
-  // pixel tile: TW x TH = 128 with TW the smallest power of two covering min(W, 128)
-  int TW = 8;
-  while (TW < d.W && TW < kBM) TW <<= 1;
-  const int TH = kBM / TW;
+  // ---- tile shape and A-staging mode
   Params p;
-  p.B = d.B; p.H = d.H; p.W = d.W; p.TW = TW; p.TH = TH;
+  p.B = d.B; p.H = d.H; p.W = d.W;
+  p.kh = d.kh; p.kw = d.kw; p.ph = d.kh / 2; p.pw = d.kw / 2; p.stride = stride;
+  int mode = MODE_TAP;
+  if (stride == 1 && (d.flags & RNC_CONV_NO_HALO) == 0) {
+    if (d.kw > 1 && d.W > 64) mode = MODE_ROWHALO;                 // one image row x 128 px per tile
+    else if (d.kw == 1 && d.kh > 1 && d.W >= 16 && d.H >= 8) mode = MODE_COLHALO;
+  }
+  int TW, TH, box_w, box_h;
+  if (mode == MODE_ROWHALO) { TW = 128; TH = 1; box_w = 136; box_h = 1; }
+  else if (mode == MODE_COLHALO) { TW = 16; TH = 8; box_w = 16; box_h = TH + 2 * p.ph; }
+  else {
+    TW = 8;
+    while (TW < d.W && TW < kBM) TW <<= 1;
+    TH = kBM / TW; box_w = TW; box_h = TH;
+  }
+  if (box_w * box_h > 256 - 8 && mode == MODE_COLHALO) return RNC_ERR_UNSUPPORTED;   // kh <= 9
+  p.mode = mode; p.TW = TW; p.TH = TH;
+  // Measured on B200: with 1024-byte-aligned stages the 128B swizzle is a function of the absolute shared-memory address,
+  // so a descriptor whose start is shifted by kx rows (kx*128 B) needs NO base_offset; setting it breaks the result.
+  p.use_base_offset = (d.flags & RNC_CONV_BASE_OFFSET) ? 1 : 0;
   p.tiles_x = (d.W + TW - 1) / TW; p.tiles_y = (d.H + TH - 1) / TH;
-  p.kw = d.kw; p.ph = d.kh / 2; p.pw = d.kw / 2; p.ntaps = ntaps;
+  p.ntiles = d.B * p.tiles_x * p.tiles_y; p.ntn = d.coutpad / bn;
+  p.a_plane = box_w * box_h * 128;
   p.nblk0 = nblk0; p.nblk = nblk;
   p.cout = d.cout; p.epilogue = d.epilogue; p.unscale = d.unscale; p.bias = d.bias;
   p.out_f32 = d.out_f32; p.ldo_f32 = d.ldo_f32;
   p.out_hi = static_cast<__half*>(d.out_hi); p.out_lo = static_cast<__half*>(d.out_lo); p.ldo_split = d.ldo_split;
-  p.h = d.h; p.ldh = d.ldh; p.aux0 = d.aux0; p.ldaux = d.ldaux;
+  p.h = d.h; p.ldh = d.ldh; p.aux0 = d.aux0; p.ldaux = d.ldaux; p.res = d.res; p.ldres = d.ldres;
 
   CUtensorMap maps[6];
-  bool ok = make_act_map(&maps[0], d.in0_hi, d.c0, d.ld0, d.B, d.H, d.W, TW, TH) &&
-            make_act_map(&maps[1], d.in0_lo, d.c0, d.ld0, d.B, d.H, d.W, TW, TH);
+  bool ok = make_in_map(&maps[0], d.in0_hi, d.c0, d.ld0, d.B, Hin, Win, box_w, box_h, stride) &&
+            make_in_map(&maps[1], d.in0_lo, d.c0, d.ld0, d.B, Hin, Win, box_w, box_h, stride);
   if (d.c1 > 0) {
-    ok = ok && make_act_map(&maps[2], d.in1_hi, d.c1, d.ld1, d.B, d.H, d.W, TW, TH) &&
-         make_act_map(&maps[3], d.in1_lo, d.c1, d.ld1, d.B, d.H, d.W, TW, TH);
+    ok = ok && make_in_map(&maps[2], d.in1_hi, d.c1, d.ld1, d.B, Hin, Win, box_w, box_h, stride) &&
+         make_in_map(&maps[3], d.in1_lo, d.c1, d.ld1, d.B, Hin, Win, box_w, box_h, stride);
   } else {
     maps[2] = maps[0]; maps[3] = maps[1];
   }
   ok = ok && make_w_map(&maps[4], d.w_hi, d.ktot, d.coutpad, bn) && make_w_map(&maps[5], d.w_lo, d.ktot, d.coutpad, bn);
   if (!ok) return RNC_ERR_BAD_SHAPE;
 
-  const int ntiles = d.B * p.tiles_x * p.tiles_y, gn = d.coutpad / bn;
   cudaStream_t s = as_stream(stream);
   switch (bn) {
-    case 32: return launch<32>(maps, p, ntiles, gn, s);
-    case 64: return launch<64>(maps, p, ntiles, gn, s);
-    case 128: return launch<128>(maps, p, ntiles, gn, s);
-    case 192: return launch<192>(maps, p, ntiles, gn, s);
-    default: return launch<256>(maps, p, ntiles, gn, s);
+    case 32: return launch<32>(maps, p, s);
+    case 64: return launch<64>(maps, p, s);
+    case 128: return launch<128>(maps, p, s);
+    case 192: return launch<192>(maps, p, s);
+    default: return launch<256>(maps, p, s);
   }
 }

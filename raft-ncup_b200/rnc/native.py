@@ -10,9 +10,10 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librnc.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
-EPI_LINEAR, EPI_RELU, EPI_SIGMOID, EPI_GRU_ZR, EPI_GRU_Q, EPI_RELU_FLOW = range(6)
+EPI_LINEAR, EPI_RELU, EPI_SIGMOID, EPI_GRU_ZR, EPI_GRU_Q, EPI_RELU_FLOW, EPI_RELU_ADD_RELU, EPI_TANH_RELU = range(8)
+CONV_NO_HALO, CONV_BASE_OFFSET = 1, 2
 
 _vp, _i, _f = C.c_void_p, C.c_int, C.c_float
 
@@ -48,7 +49,9 @@ class UmmaConvDesc(C.Structure):
                 ("h", _vp), ("ldh", _i),
                 ("aux0", _vp), ("ldaux", _i),
                 ("B", _i), ("H", _i), ("W", _i),
-                ("cout", _i), ("kh", _i), ("kw", _i), ("epilogue", _i)]
+                ("cout", _i), ("kh", _i), ("kw", _i), ("epilogue", _i),
+                ("stride", _i), ("hin", _i), ("win", _i),
+                ("res", _vp), ("ldres", _i), ("flags", _i)]
 
 
 # name -> (restype, argtypes); every symbol include/rnc.h declares
