@@ -170,6 +170,27 @@ int rnc_f32_to_split(const float* src, int lds, int C, long long M, void* dst_hi
 int rnc_conv_flow7x7_fwd(const float* coords1, const float* weight, const float* bias, int B, int H, int W,
                          int cout, float* out, int ldo, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * C6  BasicEncoder pieces (core/extractor.py:118-192) that are not wide convolutions; the 3x3/1x1 layers run on
+ * rnc_conv2d_umma_fwd (stride 1/2, RELU / RELU_ADD_RELU / TANH_RELU epilogues).
+ */
+/* Image normalisation 2*(x/255)-1 (raft_nc_dbl.py:118-119) + conv1 = Conv2d(3,64,7,stride=2,padding=3) (extractor.py:135,171).
+ * img NCHW [N][3][Hin][Win] raw 0..255; weight [147 = (c*7+ky)*7+kx][64]; bias [64]; out CL [N][ceil(Hin/2)][ceil(Win/2)][64]
+ * as fp32 and/or split halves; relu != 0 applies ReLU (norm folded into the weights). */
+int rnc_stem_conv7x7s2_fwd(const float* img, const float* weight, const float* bias, int N, int Hin, int Win, int relu,
+                           float* out_f32, void* out_hi, void* out_lo, void* stream);
+/* nn.InstanceNorm2d (no affine, biased variance; extractor.py:28-33,128-129) statistics of x CL fp32 [N][P][C], C <= 128:
+ * stats = fp64 scratch [N][C][2]; mean_rstd = [N][C][2] floats (mean, 1/sqrt(var+eps)). */
+int rnc_instnorm_stats(const float* x, int N, int P, int C, float eps, double* stats, float* mean_rstd, void* stream);
+/* apply: mode 0: norm(x) -> out_f32;  1: relu(norm(x));  2: relu(res + relu(norm(x)))  (ResidualBlock.forward,
+ * extractor.py:48-56); outputs fp32 and/or split halves, all CL [N][P][C]. */
+int rnc_instnorm_apply(const float* x, const float* mean_rstd, const float* res, int N, int P, int C, int mode,
+                       float* out_f32, void* out_hi, void* out_lo, void* stream);
+/* relu(a + b) on n fp32 elements -> fp32 (optional) + split halves (block tail when the downsample branch has its own norm). */
+int rnc_add_relu_split(const float* a, const float* b, size_t n, float* out_f32, void* out_hi, void* out_lo, void* stream);
+/* Pooling half of rnc_fmap_prepare for feature maps that are already CL: fills levels 1..levels-1 of f2_pyr from level 0. */
+int rnc_fmap_pyramid(float* f2_pyr, int B, int D, int H, int W, int levels, void* stream);
+
 /* convf1 with split-halves CL output (feeds the tensor-core convf2). */
 int rnc_conv_flow7x7_split_fwd(const float* coords1, const float* weight, const float* bias, int B, int H, int W,
                                int cout, void* out_hi, void* out_lo, int ldo, void* stream);

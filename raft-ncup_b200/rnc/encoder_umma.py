@@ -1,0 +1,176 @@
+"""fnet / cnet (core/extractor.py:118-192 BasicEncoder, ResidualBlock :6-56) on the tensor-core convolution path.
+
+The wide 3x3 / 1x1 layers run on rnc_conv2d_umma_fwd (fp16 hi/lo split operands, stride 1/2); the 7x7 stem (K = 147) is an
+exact fp32 kernel fused with the image normalisation; InstanceNorm (fnet) is a statistics pass + an apply pass fused with
+ReLU / residual add / re-splitting; BatchNorm (cnet, eval mode) is folded into the convolution weights.  The encoders write
+their results straight into the loop's resident buffers: fmap1 -> f1_cl, fmap2 -> level 0 of f2_pyr, tanh(net) -> h and
+hx[:, 0:128], relu(inp) -> hx[:, 128:256] (raft_nc_dbl.py:129-140).
+"""
+import ctypes as C
+
+import torch
+
+from . import native
+from .engine import _ptr, _stream
+from .engine_umma import HX_LD, SplitBuf, UmmaWeights
+
+EPS = 1e-5
+
+
+def _fold_bn(conv, bn):
+    w, b = conv.weight.detach().float(), conv.bias.detach().float()
+    if bn is None:
+        return w, b
+    s = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+    return w * s.view(-1, 1, 1, 1), (b - bn.running_mean) * s + bn.bias.detach()
+
+
+class PackedEncoder:
+    """Kernel-ready weights of one BasicEncoder.  kind = 'instance' (fnet) or 'batch' (cnet, BN folded)."""
+
+    def __init__(self, enc):
+        self.kind = enc.norm_fn
+        if self.kind not in ("instance", "batch"):
+            raise NotImplementedError("tensor-core encoder supports the reference's two configurations: instance / batch norm")
+        bn = self.kind == "batch"
+        if bn and any(m.training for m in enc.modules() if isinstance(m, torch.nn.BatchNorm2d)):
+            raise NotImplementedError("cnet BatchNorm in training mode (batch statistics) is not built; call .eval() / freeze_bn()")
+        w, b = _fold_bn(enc.conv1, enc.norm1 if bn else None)
+        self.stem_w = w.permute(1, 2, 3, 0).reshape(147, 64).contiguous()
+        self.stem_b = b.contiguous()
+        self.blocks = []
+        for layer in (enc.layer1, enc.layer2, enc.layer3):
+            for blk in layer:
+                cin, cout = blk.conv1.in_channels, blk.conv1.out_channels
+                stride = blk.conv1.stride[0]
+                w1 = UmmaWeights(*_fold_bn(blk.conv1, blk.norm1 if bn else None), [cin])
+                w2 = UmmaWeights(*_fold_bn(blk.conv2, blk.norm2 if bn else None), [cout])
+                wd = None
+                if blk.downsample is not None:
+                    wd = UmmaWeights(*_fold_bn(blk.downsample[0], blk.norm3 if bn else None), [cin])
+                self.blocks.append((cin, cout, stride, w1, w2, wd))
+        self.head = UmmaWeights(enc.conv2.weight, enc.conv2.bias, [128])
+
+
+class EncoderBuffers:
+    """Scratch for one encoder pass over N images of Hin x Win (three resolution levels)."""
+
+    def __init__(self, device, N, Hin, Win):
+        self.key = (str(device), N, Hin, Win)
+        f = dict(dtype=torch.float32, device=device)
+        self.dims = []
+        h, w = (Hin + 1) // 2, (Win + 1) // 2
+        for c in (64, 96, 128):
+            self.dims.append((h, w, c))
+            h, w = (h + 1) // 2, (w + 1) // 2
+        self.X32, self.XS, self.T32, self.AS, self.D32 = [], [], [], [], []
+        for (h, w, c) in self.dims:
+            rows = N * h * w
+            self.X32.append(torch.empty(rows, c, **f))
+            self.T32.append(torch.empty(rows, c, **f))
+            self.D32.append(torch.empty(rows, c, **f) if c != 64 else None)
+            self.XS.append(SplitBuf(rows, c, device))
+            self.AS.append(SplitBuf(rows, c, device))
+        self.stats = torch.empty(N * 128 * 2, dtype=torch.float64, device=device)
+        self.mr = torch.empty(N * 128 * 2, **f)
+
+
+class EncoderRunner:
+    def __init__(self, engine):
+        self.eng = engine
+        self.L = engine.L
+        self._packed = {}
+        self._bufs = None
+
+    def packed(self, enc):
+        from .engine import _param_key
+        key = _param_key(enc)
+        hit = self._packed.get(id(enc))
+        if hit is None or hit[0] != key:
+            hit = (key, PackedEncoder(enc))
+            self._packed[id(enc)] = hit
+        return hit[1]
+
+    def buffers(self, device, N, Hin, Win):
+        if self._bufs is None or self._bufs.key != (str(device), N, Hin, Win):
+            self._bufs = None
+            self._bufs = EncoderBuffers(device, N, Hin, Win)
+        return self._bufs
+
+    # ------------------------------------------------------------------ instance-norm helpers
+    def _norm(self, bufs, x32, N, P, Cc, mode, res=None, out32=None, split=None):
+        s = _stream()
+        native.check(self.L.rnc_instnorm_stats(_ptr(x32), N, P, Cc, EPS, _ptr(bufs.stats), _ptr(bufs.mr), s), "instnorm_stats")
+        native.check(self.L.rnc_instnorm_apply(_ptr(x32), _ptr(bufs.mr), _ptr(res), N, P, Cc, mode, _ptr(out32),
+                                               C.c_void_p(split.hi.data_ptr() if split else 0),
+                                               C.c_void_p(split.lo.data_ptr() if split else 0), s), "instnorm_apply")
+
+    def _trunk(self, pk, bufs, image, N, Hin, Win):
+        """Stem + the six residual blocks.  Leaves the 128-channel features at 1/8 resolution in bufs.XS[2] (split)."""
+        E, eng, s = native, self.eng, _stream()
+        inst = pk.kind == "instance"
+        h, w, _ = bufs.dims[0]
+        if inst:
+            native.check(self.L.rnc_stem_conv7x7s2_fwd(_ptr(image), _ptr(pk.stem_w), _ptr(pk.stem_b), N, Hin, Win, 0, _ptr(bufs.T32[0]),
+                                                       C.c_void_p(0), C.c_void_p(0), s), "stem")
+            self._norm(bufs, bufs.T32[0], N, h * w, 64, 1, out32=bufs.X32[0], split=bufs.XS[0])
+        else:
+            native.check(self.L.rnc_stem_conv7x7s2_fwd(_ptr(image), _ptr(pk.stem_w), _ptr(pk.stem_b), N, Hin, Win, 1, _ptr(bufs.X32[0]),
+                                                       _ptr(bufs.XS[0].hi), _ptr(bufs.XS[0].lo), s), "stem")
+        lvl = 0
+        for (cin, cout, stride, w1, w2, wd) in pk.blocks:
+            src = lvl
+            if stride == 2:
+                lvl += 1
+            hi_, wi_, _ = bufs.dims[src]
+            h, w, _ = bufs.dims[lvl]
+            P = h * w
+            xs_in, x32_in = bufs.XS[src], bufs.X32[src]
+            if inst:
+                eng.uconv(N, h, w, xs_in.ptrs(), cin, cin, w1, E.EPI_LINEAR, out_f32=bufs.T32[lvl].data_ptr(), ldo_f32=cout,
+                          stride=stride, hin=hi_, win=wi_)
+                self._norm(bufs, bufs.T32[lvl], N, P, cout, 1, split=bufs.AS[lvl])
+                res = x32_in
+                if wd is not None:
+                    eng.uconv(N, h, w, xs_in.ptrs(), cin, cin, wd, E.EPI_LINEAR, out_f32=bufs.T32[lvl].data_ptr(), ldo_f32=cout,
+                              stride=stride, hin=hi_, win=wi_)
+                    self._norm(bufs, bufs.T32[lvl], N, P, cout, 0, out32=bufs.D32[lvl])
+                    res = bufs.D32[lvl]
+                eng.uconv(N, h, w, bufs.AS[lvl].ptrs(), cout, cout, w2, E.EPI_LINEAR, out_f32=bufs.T32[lvl].data_ptr(), ldo_f32=cout)
+                self._norm(bufs, bufs.T32[lvl], N, P, cout, 2, res=res, out32=bufs.X32[lvl], split=bufs.XS[lvl])
+            else:
+                eng.uconv(N, h, w, xs_in.ptrs(), cin, cin, w1, E.EPI_RELU, out_split=bufs.AS[lvl].ptrs(), ldo_split=cout,
+                          stride=stride, hin=hi_, win=wi_)
+                res = x32_in
+                if wd is not None:
+                    eng.uconv(N, h, w, xs_in.ptrs(), cin, cin, wd, E.EPI_LINEAR, out_f32=bufs.D32[lvl].data_ptr(), ldo_f32=cout,
+                              stride=stride, hin=hi_, win=wi_)
+                    res = bufs.D32[lvl]
+                eng.uconv(N, h, w, bufs.AS[lvl].ptrs(), cout, cout, w2, E.EPI_RELU_ADD_RELU, out_f32=bufs.X32[lvl].data_ptr(),
+                          ldo_f32=cout, out_split=bufs.XS[lvl].ptrs(), ldo_split=cout, res=res.data_ptr(), ldres=cout)
+        return bufs.dims[2]
+
+    # ------------------------------------------------------------------ public
+    def run(self, model, ws, image1, image2):
+        """image1/image2: raw [B,3,H,W] fp32 in 0..255 (the stem normalises).  Fills ws.f1_cl, ws.f2_pyr (level 0), ws.h,
+        ws.hx[:, :256]; the caller finishes the pyramid."""
+        eng, E = self.eng, native
+        B, _, Hin, Win = image1.shape
+        dev = image1.device
+        pf, pc = self.packed(model.fnet), self.packed(model.cnet)
+        bufs = self.buffers(dev, 2 * B, Hin, Win)
+        # ---- fnet on both frames (extractor.py:168-172 concatenates them along the batch)
+        both = torch.cat([image1, image2], 0).contiguous()
+        h8, w8, _ = self._trunk(pf, bufs, both, 2 * B, Hin, Win)
+        P = h8 * w8
+        eng.alloc_fmaps(ws, B, 256, h8, w8, 4)
+        xs = bufs.XS[2]
+        eng.uconv(B, h8, w8, xs.ptrs(), 128, 128, pf.head, E.EPI_LINEAR, out_f32=ws.f1_cl.data_ptr(), ldo_f32=256)
+        off = B * P * 128 * 2                                  # second half of the batch inside the split planes (bytes)
+        eng.uconv(B, h8, w8, (xs.hi.data_ptr() + off, xs.lo.data_ptr() + off), 128, 128, pf.head, E.EPI_LINEAR,
+                  out_f32=ws.f2_pyr.data_ptr(), ldo_f32=256)
+        # ---- cnet on frame 1
+        self._trunk(pc, bufs, image1.contiguous(), B, Hin, Win)
+        eng.uconv(B, h8, w8, bufs.XS[2].ptrs(), 128, 128, pc.head, E.EPI_TANH_RELU, out_f32=ws.h.data_ptr(), ldo_f32=128,
+                  out_split=ws.hx.ptrs(), ldo_split=HX_LD)
+        return h8, w8

@@ -192,15 +192,39 @@ class UmmaEngine(Engine):
 
     def fmap_prepare(self, ws, fmap1, fmap2, levels=4):
         super().fmap_prepare(ws, fmap1, fmap2, levels)
+        self._refresh_halves(ws)     # halves copies of the CL feature map / pyramid: the tensor-core lookup's operands
+
+    # ------------------------------------------------------------------ encoders on the tensor-core path
+    def encoder(self):
+        if getattr(self, "_encoder", None) is None:
+            from .encoder_umma import EncoderRunner
+            self._encoder = EncoderRunner(self)
+        return self._encoder
+
+    def alloc_fmaps(self, ws, B, D, H, W, levels):
+        """Allocate the CL feature map / pyramid buffers that the encoder heads write into directly."""
+        total = self.L.rnc_pyramid_offset(B, D, H, W, levels)
+        if ws.f1_cl is None or ws.f1_cl.numel() != B * H * W * D:
+            dev = ws.coords1.device
+            ws.f1_cl = torch.empty(B * H * W, D, dtype=torch.float32, device=dev)
+            ws.f2_pyr = torch.empty(total, dtype=torch.float32, device=dev)
+        ws.D, ws.levels = D, levels
+
+    def finish_fmaps(self, ws):
+        """Pool fmap2 into the pyramid (corr.py:18-21 on features) and refresh the halves copies."""
+        native.check(self.L.rnc_fmap_pyramid(_ptr(ws.f2_pyr), ws.B, ws.D, ws.H8, ws.W8, ws.levels, _stream()), "fmap_pyramid")
+        self._refresh_halves(ws)
+
+    def _refresh_halves(self, ws):
         if self.lookup_mode != "umma":
             return
-        # halves copies of the CL feature map / pyramid: the tensor-core lookup's operands
         n1, n2 = ws.f1_cl.numel(), ws.f2_pyr.numel()
         if getattr(ws, "f1h", None) is None or ws.f1h.numel() != n1:
-            ws.f1h = torch.empty(n1, dtype=torch.float16, device=fmap1.device)
-            ws.f2h = torch.empty(n2, dtype=torch.float16, device=fmap1.device)
+            dev = ws.f1_cl.device
+            ws.f1h = torch.empty(n1, dtype=torch.float16, device=dev)
+            ws.f2h = torch.empty(n2, dtype=torch.float16, device=dev)
             nbytes = self.L.rnc_corr_lookup_umma_workspace_bytes(ws.B, ws.H8, ws.W8)
-            ws.lookup_flags = torch.zeros(nbytes // 4, dtype=torch.int32, device=fmap1.device)
+            ws.lookup_flags = torch.zeros(nbytes // 4, dtype=torch.int32, device=dev)
         s = _stream()
         native.check(self.L.rnc_f32_to_f16(_ptr(ws.f1_cl), _ptr(ws.f1h), n1, s), "f32_to_f16(f1)")
         native.check(self.L.rnc_f32_to_f16(_ptr(ws.f2_pyr), _ptr(ws.f2h), n2, s), "f32_to_f16(f2)")

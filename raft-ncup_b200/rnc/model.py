@@ -5,6 +5,7 @@ same ctor Namespace, ``forward(image1, image2, iters=12, flow_init=None, upsampl
 and state_dict keys.  The iteration loop runs entirely on resident channel-last buffers through librnc.so.
 """
 import ctypes as C
+import os
 from collections import OrderedDict
 
 import torch
@@ -66,19 +67,10 @@ class _RAFTBase(nn.Module):
             raise ValueError("iters must be >= 1")
         if hasattr(self, "data_idx"):
             self.data_idx += 1
-        image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
-        image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
-        amp = bool(getattr(self.args, "mixed_precision", False))
-        with torch.autocast("cuda", enabled=amp):
-            fmap1, fmap2 = self.fnet([image1, image2])
-        fmap1, fmap2 = fmap1.float().contiguous(), fmap2.float().contiguous()
-        with torch.autocast("cuda", enabled=amp):
-            cnet = self.cnet(image1)
-            net, inp = torch.split(cnet, [128, 128], dim=1)
-            net, inp = torch.tanh(net), torch.relu(inp)
-        net, inp = net.float().contiguous(), inp.float().contiguous()
-
-        B, _, H8, W8 = fmap1.shape
+        B, _, Him, Wim = image1.shape
+        if Him % 8 or Wim % 8:
+            raise ValueError("image height/width must be multiples of 8 (pad with utils.utils.InputPadder, evaluate.py:125)")
+        H8, W8 = Him // 8, Wim // 8
         eng = self.engine()
         L = eng.L
         pk = eng.packed_update(self.update_block)
@@ -87,8 +79,24 @@ class _RAFTBase(nn.Module):
             raise NotImplementedError("weights-net BatchNorm in training mode is not built; call .eval() or freeze_bn()")
         ws = eng.workspace(image1.device, B, H8, W8, pk.has_mask, self.ncup)
         s = _stream()
-        eng.fmap_prepare(ws, fmap1, fmap2, 4)
-        eng.load_state(ws, net, inp)
+        amp = bool(getattr(self.args, "mixed_precision", False))
+        if eng.mode == "umma" and not amp and os.environ.get("RNC_ENCODER", "umma").lower() == "umma":
+            # encoders on the tensor-core path, writing straight into the resident buffers (raft_nc_dbl.py:118-140)
+            eng.encoder().run(self, ws, image1.float().contiguous(), image2.float().contiguous())
+            eng.finish_fmaps(ws)
+        else:
+            image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
+            image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
+            with torch.autocast("cuda", enabled=amp):
+                fmap1, fmap2 = self.fnet([image1, image2])
+            fmap1, fmap2 = fmap1.float().contiguous(), fmap2.float().contiguous()
+            with torch.autocast("cuda", enabled=amp):
+                cnet = self.cnet(image1)
+                net, inp = torch.split(cnet, [128, 128], dim=1)
+                net, inp = torch.tanh(net), torch.relu(inp)
+            net, inp = net.float().contiguous(), inp.float().contiguous()
+            eng.fmap_prepare(ws, fmap1, fmap2, 4)
+            eng.load_state(ws, net, inp)
         fi = None
         if flow_init is not None:
             fi = flow_init.to(image1.device).float().contiguous()
