@@ -20,7 +20,7 @@
 namespace rnc {
 namespace umma {
 
-constexpr int kThreads = 192;        // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kThreads = 320;        // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue (2 per lane group)
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kMaxSA = 4, kMaxSB = 8;
@@ -65,7 +65,12 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
 template <int BN>
 struct Cfg {
   static constexpr int kBTile = BN * kBK * 2;                     // bytes per half-plane of weights
-  static constexpr int kTmemCols = BN <= 32 ? 64 : BN <= 64 ? 128 : BN <= 128 ? 256 : 512;   // two accumulators
+  // Each tile owns TWO accumulators: `main` takes the x_hi*w_hi products, `corr` the two 2^-11-smaller cross terms.
+  // The tensor core truncates on every accumulate, so the error grows with the number of full-magnitude adds; keeping
+  // the cross terms out of `main` cuts it 3x (measured: 4.8e-5 -> 1.7e-5 on a 3x3x256 layer).  BN <= 128 double-buffers
+  // the pair (epilogue overlaps the next tile's main loop); wider tiles fit only one pair in the 512 TMEM columns.
+  static constexpr int kBufs = BN <= 128 ? 2 : 1;
+  static constexpr int kTmemCols = BN <= 32 ? 128 : BN <= 64 ? 256 : 512;
 };
 
 template <int BN>
@@ -97,7 +102,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
@@ -150,10 +155,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
       const int shift_rows = p.mode == MODE_ROWHALO ? 1 : p.mode == MODE_COLHALO ? p.TW : 0;
       int a_it = 0, b_it = 0, t_it = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++t_it) {
-        const int buf = t_it & 1, use = t_it >> 1;
+        const int buf = t_it % C::kBufs, use = t_it / C::kBufs;
         mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * BN;
+        const uint32_t d_main = tmem_base + buf * 2 * BN, d_corr = d_main + BN;
         uint32_t acc = 0;
         for (int g = 0; g < G; ++g)
           for (int cb = 0; cb < p.nblk; ++cb) {
@@ -172,10 +177,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
               const uint64_t bh = smem_desc_sw128(br), bl = smem_desc_sw128(br + C::kBTile);
 #pragma unroll
               for (int k = 0; k < kBK / 16; ++k) {
-                umma_f16(d_tmem, ah + 2 * k, bh + 2 * k, idesc, acc);
+                umma_f16(d_main, ah + 2 * k, bh + 2 * k, idesc, acc);
+                umma_f16(d_corr, ah + 2 * k, bl + 2 * k, idesc, acc);
                 acc = 1;
-                umma_f16(d_tmem, ah + 2 * k, bl + 2 * k, idesc, 1);
-                umma_f16(d_tmem, al + 2 * k, bh + 2 * k, idesc, 1);
+                umma_f16(d_corr, al + 2 * k, bh + 2 * k, idesc, 1);
               }
               umma_commit(&b_empty[sb]);
             }
@@ -196,24 +201,29 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
       const int y = (tr / p.tiles_x) * p.TH + ml / p.TW, x = (tr % p.tiles_x) * p.TW + ml % p.TW;
       const bool valid = y < p.H && x < p.W;
       const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
-      const int buf = t_it & 1, use = t_it >> 1;
+      const int buf = t_it % C::kBufs, use = t_it / C::kBufs;
       mbar_wait(&acc_full[buf], use & 1);
       tcgen05_fence_after();
+      // two epilogue warps per TMEM lane group: the first takes the lower half of the 32-channel chunks, the second the rest
+      constexpr int kChunksN = BN / 32, kHalfN = (kChunksN + 1) / 2;
+      const int cc0 = (warp - 2) < 4 ? 0 : kHalfN, cc1 = (warp - 2) < 4 ? kHalfN : kChunksN;
 #pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
+      for (int cc = cc0; cc < cc1; ++cc) {
         const int n = n0 + cc * 32;
         if (n >= p.cout + (epi == RNC_EPI_RELU_FLOW ? 2 : 0)) break;   // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + buf * BN + cc * 32, r);
+        uint32_t r[32], rc[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + buf * 2 * BN + cc * 32;
+        tmem_ld32(taddr, r);
+        tmem_ld32(taddr + BN, rc);
         if (!valid) continue;
         float v[32];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n) + q);
-          v[4 * q + 0] = fmaf(__uint_as_float(r[4 * q + 0]), p.unscale, bv.x);
-          v[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]), p.unscale, bv.y);
-          v[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]), p.unscale, bv.z);
-          v[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]), p.unscale, bv.w);
+          v[4 * q + 0] = fmaf(__uint_as_float(r[4 * q + 0]) + __uint_as_float(rc[4 * q + 0]), p.unscale, bv.x);
+          v[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]) + __uint_as_float(rc[4 * q + 1]), p.unscale, bv.y);
+          v[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]) + __uint_as_float(rc[4 * q + 2]), p.unscale, bv.z);
+          v[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]) + __uint_as_float(rc[4 * q + 3]), p.unscale, bv.w);
         }
         if (epi == RNC_EPI_GRU_ZR) {
           const int Ch = p.cout >> 1;
