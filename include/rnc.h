@@ -73,7 +73,10 @@ int rnc_corr_lookup_fwd(const float* f1_cl, const float* f2_pyr, const float* co
  * format of rnc_conv2d_umma_fwd, so the 1x1 convc1 (update.py:82,90) consumes it without a conversion pass. */
 int rnc_corr_lookup_split_fwd(const float* f1_cl, const float* f2_pyr, const float* coords,
                               int B, int D, int H, int W, int levels, int radius,
-                              void* out_hi, void* out_lo, int ldo, void* stream);
+                              void* out_hi, void* out_lo, int ldo, int lvl_stride, void* stream);
+/* lvl_stride: channels reserved per pyramid level in the output row (>= 81; level l starts at l*lvl_stride, the
+ * channels [81, lvl_stride) of each level are written as zeros).  The tensor-core path uses 88 so that every 8-channel
+ * group is one aligned 16-byte store and convc1's K stays 6 blocks of 64. */
 
 /* Tensor-core version of the lookup (tcgen05 + TMA; same reference code, corr.py:7-55 + utils.py:59-73).
  *   f1h_cl / f2h_pyr : the CL feature map / pyramid of rnc_fmap_prepare rounded once to halves (rnc_f32_to_f16), same
@@ -87,7 +90,8 @@ int rnc_corr_lookup_split_fwd(const float* f1_cl, const float* f2_pyr, const flo
 size_t rnc_corr_lookup_umma_workspace_bytes(int B, int H, int W);
 int rnc_corr_lookup_umma_fwd(const void* f1h_cl, const void* f2h_pyr, const float* f1_cl, const float* f2_pyr,
                              const float* coords, int B, int D, int H, int W, int levels, int radius,
-                             void* out_hi, void* out_lo, int ldo, void* workspace, size_t workspace_bytes, void* stream);
+                             void* out_hi, void* out_lo, int ldo, int lvl_stride, void* workspace, size_t workspace_bytes,
+                             void* stream);   /* lvl_stride must be 88 */
 /* fp32 -> fp16 (round to nearest), n % 4 == 0. */
 int rnc_f32_to_f16(const float* src, void* dst, size_t n, void* stream);
 

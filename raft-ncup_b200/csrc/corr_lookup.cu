@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 corr_lookup_tile_kernel(const float* __restrict__ f1_cl, const float* __restrict__ f2_pyr,
                         const float* __restrict__ coords, int B, int D, int H, int W, int levels,
                         float* __restrict__ out, int layout, int ldo, __half* __restrict__ out_lo,
-                        const int* __restrict__ flags, int ftx, int fty) {
+                        const int* __restrict__ flags, int ftx, int fty, int lvl_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LookupSmem& sm = *reinterpret_cast<LookupSmem*>(smem_raw);
 
@@ -177,13 +177,17 @@ corr_lookup_tile_kernel(const float* __restrict__ f1_cl, const float* __restrict
       if (layout == 0)
         out[(((size_t)b * K + l * kS * kS + k) * H + qy) * W + qx] = v;
       else if (layout == 1)
-        out[((size_t)b * P + qy * W + qx) * ldo + l * kS * kS + k] = v;
+        out[((size_t)b * P + qy * W + qx) * ldo + l * lvl_stride + k] = v;
       else {   // layout 2: exact hi/lo split halves planes (input format of the tcgen05 convolutions)
-        const size_t idx = ((size_t)b * P + qy * W + qx) * ldo + l * kS * kS + k;
+        const size_t idx = ((size_t)b * P + qy * W + qx) * ldo + l * lvl_stride + k;
         const float vc = fminf(fmaxf(v, -65504.f), 65504.f);
         const __half hi = __float2half_rn(vc);
         reinterpret_cast<__half*>(out)[idx] = hi;
         out_lo[idx] = __float2half_rn(vc - __half2float(hi));
+        if (k < lvl_stride - kS * kS) {          // zero the pad channels of the level (tensor-core consumers read them)
+          reinterpret_cast<__half*>(out)[idx - k + kS * kS + k] = __float2half_rn(0.f);
+          out_lo[idx - k + kS * kS + k] = __float2half_rn(0.f);
+        }
       }
     }
     __syncthreads();
@@ -197,28 +201,28 @@ using namespace rnc;
 static int lookup_launch(const float* f1_cl, const float* f2_pyr, const float* coords,
                          int B, int D, int H, int W, int levels, int radius,
                          float* out, int layout, int ldo, __half* out_lo, void* stream,
-                         const int* flags = nullptr, int ftx = 0, int fty = 0) {
+                         const int* flags = nullptr, int ftx = 0, int fty = 0, int lvl_stride = kS * kS) {
   if (B <= 0 || H <= 0 || W <= 0 || D <= 0 || (D % kChunk) != 0) return RNC_ERR_BAD_SHAPE;
   if (levels < 1 || levels > 4 || (H >> (levels - 1)) < 1 || (W >> (levels - 1)) < 1) return RNC_ERR_BAD_SHAPE;
   if (radius != kR) return RNC_ERR_UNSUPPORTED;
   if (layout < 0 || layout > 2) return RNC_ERR_BAD_SHAPE;
-  if (layout >= 1 && ldo < levels * kS * kS) return RNC_ERR_BAD_SHAPE;
+  if (lvl_stride < kS * kS || (layout >= 1 && ldo < levels * lvl_stride)) return RNC_ERR_BAD_SHAPE;
   if (layout == 2 && !out_lo) return RNC_ERR_BAD_POINTER;
   if (!f1_cl || !f2_pyr || !coords || !out || !aligned16(f1_cl) || !aligned16(f2_pyr)) return RNC_ERR_BAD_POINTER;
   static unsigned long long attr_done = 0;
   if (int st = ensure_dyn_smem(corr_lookup_tile_kernel, (int)sizeof(LookupSmem), &attr_done)) return st;
   dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, B);
   corr_lookup_tile_kernel<<<grid, kThreads, sizeof(LookupSmem), as_stream(stream)>>>(
-      f1_cl, f2_pyr, coords, B, D, H, W, levels, out, layout, ldo, out_lo, flags, ftx, fty);
+      f1_cl, f2_pyr, coords, B, D, H, W, levels, out, layout, ldo, out_lo, flags, ftx, fty, lvl_stride);
   return after_launch();
 }
 
 // used by corr_lookup_umma.cu
 int rnc_corr_lookup_fallback_split(const float* f1_cl, const float* f2_pyr, const float* coords, int B, int D, int H, int W,
-                                   int levels, void* out_hi, void* out_lo, int ldo, const int* flags, int flag_tiles_x,
-                                   int flag_tiles_y, void* stream) {
+                                   int levels, void* out_hi, void* out_lo, int ldo, int lvl_stride, const int* flags,
+                                   int flag_tiles_x, int flag_tiles_y, void* stream) {
   return lookup_launch(f1_cl, f2_pyr, coords, B, D, H, W, levels, kR, static_cast<float*>(out_hi), 2, ldo,
-                       static_cast<__half*>(out_lo), stream, flags, flag_tiles_x, flag_tiles_y);
+                       static_cast<__half*>(out_lo), stream, flags, flag_tiles_x, flag_tiles_y, lvl_stride);
 }
 
 extern "C" int rnc_corr_lookup_fwd(const float* f1_cl, const float* f2_pyr, const float* coords,
@@ -230,7 +234,7 @@ extern "C" int rnc_corr_lookup_fwd(const float* f1_cl, const float* f2_pyr, cons
 
 extern "C" int rnc_corr_lookup_split_fwd(const float* f1_cl, const float* f2_pyr, const float* coords,
                                          int B, int D, int H, int W, int levels, int radius,
-                                         void* out_hi, void* out_lo, int ldo, void* stream) {
+                                         void* out_hi, void* out_lo, int ldo, int lvl_stride, void* stream) {
   return lookup_launch(f1_cl, f2_pyr, coords, B, D, H, W, levels, radius, static_cast<float*>(out_hi), 2, ldo,
-                       static_cast<__half*>(out_lo), stream);
+                       static_cast<__half*>(out_lo), stream, nullptr, 0, 0, lvl_stride);
 }

@@ -40,11 +40,11 @@ constexpr int kChunks = 3 + 3 + 1 + 1;
 constexpr int kStages = 3;
 constexpr int kATile = 128 * 64 * 2;     // 16 KB per K block
 constexpr int kBStage = 256 * 64 * 2;    // 32 KB: 256 positions x 64 halves
-constexpr int kStagePitch = 81;
+constexpr int kLvlStride = 88;           // channels per level in the output row (81 taps + 7 zero pads): 16-byte groups
 constexpr int kSmemA = kKB * kATile;                         // 64 KB
 constexpr int kSmemB = kStages * kBStage;                    // 96 KB
 constexpr int kSmemScratch = 32 * 128 * 4;                   // 16 KB
-constexpr int kSmemStage = 128 * kStagePitch * 4;            // 41.5 KB
+constexpr int kSmemStage = 128 * 81 * 4;                     // 41.5 KB, [tap][pixel]
 constexpr int kSmemTotal = kSmemA + kSmemB + kSmemScratch + kSmemStage + 1024 + 512;
 
 struct Params {
@@ -65,7 +65,7 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
                         const __grid_constant__ CUtensorMap mL1, const __grid_constant__ CUtensorMap mL2,
                         const __grid_constant__ CUtensorMap mL3, const Params p) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned, stays in the shared window
   unsigned char* sA = smem;
   unsigned char* sB = smem + kSmemA;
   float* scratch = reinterpret_cast<float*>(smem + kSmemA + kSmemB);
@@ -190,9 +190,8 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
     }
   } else {
     // ------------------------------------------------------------------ epilogue: gather + bilinear blend + store
-    const int et = threadIdx.x - 64;                 // 0..127 within the epilogue group
     float* my_scratch = scratch + ml;                // [col][128] layout: thread-private column, conflict free
-    float* my_stage = stage + ml * kStagePitch;
+    float* my_stage = stage + ml;                    // [channel][128] layout, thread-private column
     int ch = 0;
     float inv = 1.f;
 #pragma unroll 1
@@ -208,44 +207,60 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
       const int ox = ix0 - (any ? ti->bx0[l] : 0), oy = iy0 - (any ? ti->by0[l] : 0);
       const bool live = valid && !empty;
       if (valid && empty) {
-        for (int k = 0; k < kS * kS; ++k) my_stage[k] = 0.f;
+        for (int k = 0; k < kS * kS; ++k) my_stage[k * 128] = 0.f;
       }
       const int bw = box_w(l), cr = chunk_rows(l);
       float hprev[kS];
 #pragma unroll
       for (int i = 0; i < kS; ++i) hprev[i] = 0.f;
+      // warp-uniform ranges of the box rows / columns that any pixel of this warp (2 tile rows) actually needs
+      const int row_lo = __reduce_min_sync(0xffffffffu, live ? oy : 0x7fffffff);
+      const int row_hi = __reduce_max_sync(0xffffffffu, live ? oy + kG - 1 : -1);
+      const int col_lo = __reduce_min_sync(0xffffffffu, live ? ox : 0x7fffffff);
+      const int col_hi = __reduce_max_sync(0xffffffffu, live ? ox + kG - 1 : -1);
+      // one box row: park the needed columns in the thread-private scratch column, gather the pixel's 10 lattice values,
+      // interpolate in x, blend with the previous row in y -> 9 outputs of window row j = cidx - 1
+      auto process_row = [&](const uint32_t* v, int ncols, int box_row) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q)
+          if (q < ncols && q >= col_lo && q <= col_hi) my_scratch[q * 128] = __uint_as_float(v[q]);
+        const int cidx = box_row - oy;               // lattice row (y) of this pixel's window held by this box row
+        if (live && cidx >= 0 && cidx < kG) {
+          float g[kG];
+#pragma unroll
+          for (int a = 0; a < kG; ++a) g[a] = my_scratch[(ox + a) * 128];
+          float h[kS];
+#pragma unroll
+          for (int i = 0; i < kS; ++i) h[i] = (1.f - ax) * g[i] + ax * g[i + 1];
+          if (cidx >= 1) {
+            const int j = cidx - 1;
+#pragma unroll
+            for (int i = 0; i < kS; ++i) my_stage[(i * kS + j) * 128] = ((1.f - ay) * hprev[i] + ay * h[i]) * p.scale;
+          }
+#pragma unroll
+          for (int i = 0; i < kS; ++i) hprev[i] = h[i];
+        }
+      };
       for (int c = 0; c < n_chunks(l); ++c, ++ch) {
         const int buf = ch & 1, use = ch >> 1;
         mbar_wait(&acc_full[buf], use & 1);
         tcgen05_fence_after();
-        for (int r = 0; r < cr; ++r) {
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + buf * 256 + r * bw;
-          if (bw == 32) {
-            uint32_t v[32];
-            tmem_ld32(taddr, v);
-#pragma unroll
-            for (int q = 0; q < 32; ++q) my_scratch[q * 128] = __uint_as_float(v[q]);
-          } else {
-            uint32_t v[16];
-            tmem_ld16(taddr, v);
-#pragma unroll
-            for (int q = 0; q < 16; ++q) my_scratch[q * 128] = __uint_as_float(v[q]);
-          }
-          const int cidx = c * cr + r - oy;          // lattice row (y) of this pixel's window held by this box row
-          if (live && cidx >= 0 && cidx < kG) {
-            float g[kG];
-#pragma unroll
-            for (int a = 0; a < kG; ++a) g[a] = my_scratch[(ox + a) * 128];
-            float h[kS];
-#pragma unroll
-            for (int i = 0; i < kS; ++i) h[i] = (1.f - ax) * g[i] + ax * g[i + 1];
-            if (cidx >= 1) {
-              const int j = cidx - 1;
-#pragma unroll
-              for (int i = 0; i < kS; ++i) my_stage[i * kS + j] = ((1.f - ay) * hprev[i] + ay * h[i]) * p.scale;
+        const int r0 = max(0, row_lo - c * cr), r1 = min(cr - 1, row_hi - c * cr);   // rows of this chunk the warp needs
+        const uint32_t tbase = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + buf * 256;
+        if (r0 <= r1) {
+          // software pipeline: the TMEM load of row r+1 is in flight while row r is processed
+          uint32_t va[32] = {}, vb[32] = {};
+          if (bw == 32) tmem_ld32_issue(tbase + r0 * 32, va); else tmem_ld16_issue(tbase + r0 * 16, va);
+          tmem_ld_wait32(va);
+          for (int r = r0; r <= r1; r += 2) {
+            if (r + 1 <= r1) { if (bw == 32) tmem_ld32_issue(tbase + (r + 1) * 32, vb); else tmem_ld16_issue(tbase + (r + 1) * 16, vb); }
+            process_row(va, bw, c * cr + r);
+            tmem_ld_wait32(vb);
+            if (r + 1 <= r1) {
+              if (r + 2 <= r1) { if (bw == 32) tmem_ld32_issue(tbase + (r + 2) * 32, va); else tmem_ld16_issue(tbase + (r + 2) * 16, va); }
+              process_row(vb, bw, c * cr + r + 1);
+              tmem_ld_wait32(va);
             }
-#pragma unroll
-            for (int i = 0; i < kS; ++i) hprev[i] = h[i];
           }
         }
         // all of this warp's reads of the TMEM buffer are complete (tcgen05.wait::ld inside tmem_ld*)
@@ -254,18 +269,30 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
       }
       // ---- level done: coalesced write-out of 128 px x 81 taps as hi/lo halves
-      named_bar_sync(1, 128);
-      for (int e = et; e < 128 * kS * kS; e += 128) {
-        const int q = e / (kS * kS), k = e - q * (kS * kS);
+      // The level occupies kLvlStride (= 88, a multiple of 8) channels of the output row: 81 taps + 7 zero pads, so
+      // every group of 8 channels is one aligned 16-byte store per plane.  Thread = pixel; staging is [channel][pixel].
+      {
+        const int q = ml;        // staging column is thread-private (written and read by the same thread): no barrier
         const int qy = y0 + (q >> 4), qx = x0 + (q & 15);
-        if (qy >= p.H || qx >= p.W) continue;
-        const float v = fminf(fmaxf(stage[q * kStagePitch + k], -65504.f), 65504.f);
-        const size_t idx = (static_cast<size_t>(b) * HW + qy * p.W + qx) * p.ldo + l * kS * kS + k;
-        const __half hi = __float2half_rn(v);
-        p.out_hi[idx] = hi;
-        p.out_lo[idx] = __float2half_rn(v - __half2float(hi));
+        if (qy < p.H && qx < p.W) {
+          const size_t base = (static_cast<size_t>(b) * HW + qy * p.W + qx) * p.ldo + l * kLvlStride;
+#pragma unroll 1
+          for (int gq = 0; gq < kLvlStride / 8; ++gq) {
+            __half2 hh[4], ll[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int k0 = gq * 8 + 2 * j;
+              float v0 = k0 < kS * kS ? stage[k0 * 128 + q] : 0.f, v1 = k0 + 1 < kS * kS ? stage[(k0 + 1) * 128 + q] : 0.f;
+              v0 = fminf(fmaxf(v0, -65504.f), 65504.f); v1 = fminf(fmaxf(v1, -65504.f), 65504.f);
+              const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+              hh[j] = __halves2half2(h0, h1);
+              ll[j] = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+            }
+            *reinterpret_cast<uint4*>(p.out_hi + base + gq * 8) = *reinterpret_cast<uint4*>(hh);
+            *reinterpret_cast<uint4*>(p.out_lo + base + gq * 8) = *reinterpret_cast<uint4*>(ll);
+          }
+        }
       }
-      named_bar_sync(1, 128);
     }
   }
 
@@ -310,18 +337,18 @@ extern "C" size_t rnc_corr_lookup_umma_workspace_bytes(int B, int H, int W) {
 
 // defined in corr_lookup.cu: exact kernel restricted to flagged 8x16 tiles, split-halves output
 int rnc_corr_lookup_fallback_split(const float* f1_cl, const float* f2_pyr, const float* coords, int B, int D, int H, int W,
-                                   int levels, void* out_hi, void* out_lo, int ldo, const int* flags, int flag_tiles_x,
-                                   int flag_tiles_y, void* stream);
+                                   int levels, void* out_hi, void* out_lo, int ldo, int lvl_stride, const int* flags,
+                                   int flag_tiles_x, int flag_tiles_y, void* stream);
 
 extern "C" int rnc_corr_lookup_umma_fwd(const void* f1h_cl, const void* f2h_pyr, const float* f1_cl, const float* f2_pyr,
                                         const float* coords, int B, int D, int H, int W, int levels, int radius,
-                                        void* out_hi, void* out_lo, int ldo, void* workspace, size_t workspace_bytes,
-                                        void* stream) {
+                                        void* out_hi, void* out_lo, int ldo, int lvl_stride, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
   using namespace lookup_umma;
   using namespace rnc::umma;
   if (B <= 0 || H <= 0 || W <= 0) return RNC_ERR_BAD_SHAPE;
   if (D != kD || levels != kLevels || radius != kR) return RNC_ERR_UNSUPPORTED;
-  if ((H >> (levels - 1)) < 1 || (W >> (levels - 1)) < 1 || ldo < levels * kS * kS) return RNC_ERR_BAD_SHAPE;
+  if ((H >> (levels - 1)) < 1 || (W >> (levels - 1)) < 1 || ldo < levels * kLvlStride || (ldo & 7) || lvl_stride != kLvlStride) return RNC_ERR_BAD_SHAPE;
   if (!f1h_cl || !f2h_pyr || !f1_cl || !f2_pyr || !coords || !out_hi || !out_lo || !workspace) return RNC_ERR_BAD_POINTER;
   if (!aligned16(f1h_cl) || !aligned16(f2h_pyr)) return RNC_ERR_BAD_POINTER;
   if (workspace_bytes < rnc_corr_lookup_umma_workspace_bytes(B, H, W)) return RNC_ERR_WORKSPACE;
@@ -351,6 +378,6 @@ extern "C" int rnc_corr_lookup_umma_fwd(const void* f1h_cl, const void* f2h_pyr,
   corr_lookup_umma_kernel<<<ntiles, kThreads, kSmemTotal, as_stream(stream)>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
   if (int st = after_launch()) return st;
   // exact recomputation of the tiles the fixed boxes could not cover
-  return rnc_corr_lookup_fallback_split(f1_cl, f2_pyr, coords, B, D, H, W, levels, out_hi, out_lo, ldo, p.flags, p.tiles_x,
-                                        p.tiles_y, stream);
+  return rnc_corr_lookup_fallback_split(f1_cl, f2_pyr, coords, B, D, H, W, levels, out_hi, out_lo, ldo, lvl_stride, p.flags,
+                                        p.tiles_x, p.tiles_y, stream);
 }

@@ -12,7 +12,16 @@ from . import native
 from .engine import CORR_CH, HX_LD, Engine, PackedUpsampler, _ptr, _stream, _Timed, pack_thin
 from .native import UmmaConvDesc
 
-CORR_LD = 328          # 324 padded so that the row pitch of the halves planes is a multiple of 16 B
+CORR_LS = 88           # channels reserved per pyramid level in the resident corr row: 81 taps + 7 zero pads (16-byte groups)
+CORR_LD = 4 * CORR_LS  # 352: row pitch of the corr halves planes; convc1 still needs only 6 K-blocks of 64
+
+
+def expand_corr_weight(weight):
+    """convc1 weight [Cout, 324, 1, 1] -> [Cout, 352, 1, 1] in the padded per-level layout (zeros at the pads)."""
+    w = torch.zeros(weight.shape[0], CORR_LD, 1, 1, dtype=torch.float32, device=weight.device)
+    for lvl in range(4):
+        w[:, lvl * CORR_LS: lvl * CORR_LS + 81] = weight.detach().float()[:, lvl * 81:(lvl + 1) * 81]
+    return w
 GIN_LD = 136           # 2 + 128 (+2 zero) channels of the weights-net input, pitch multiple of 16 B
 
 
@@ -59,7 +68,7 @@ class PackedUpdateUmma:
     def __init__(self, ub):
         e, g, fh = ub.encoder, ub.gru, ub.flow_head
         cat = torch.cat
-        self.convc1 = UmmaWeights(e.convc1.weight, e.convc1.bias, [CORR_CH])
+        self.convc1 = UmmaWeights(expand_corr_weight(e.convc1.weight), e.convc1.bias, [CORR_LD])
         self.convc2 = UmmaWeights(e.convc2.weight, e.convc2.bias, [256])
         self.convf1 = (pack_thin(e.convf1.weight), e.convf1.bias.detach().float().contiguous())
         self.convf2 = UmmaWeights(e.convf2.weight, e.convf2.bias, [128])
@@ -235,12 +244,12 @@ class UmmaEngine(Engine):
             with _Timed(self, "corr_lookup"):
                 native.check(self.L.rnc_corr_lookup_umma_fwd(
                     _ptr(ws.f1h), _ptr(ws.f2h), _ptr(ws.f1_cl), _ptr(ws.f2_pyr), _ptr(ws.coords1), ws.B, ws.D, ws.H8, ws.W8,
-                    ws.levels, 4, _ptr(ws.corr.hi), _ptr(ws.corr.lo), CORR_LD, _ptr(ws.lookup_flags),
+                    ws.levels, 4, _ptr(ws.corr.hi), _ptr(ws.corr.lo), CORR_LD, CORR_LS, _ptr(ws.lookup_flags),
                     ws.lookup_flags.numel() * 4, _stream()), "corr_lookup_umma")
             return
         with _Timed(self, "corr_lookup"):
             native.check(self.L.rnc_corr_lookup_split_fwd(_ptr(ws.f1_cl), _ptr(ws.f2_pyr), _ptr(ws.coords1), ws.B, ws.D, ws.H8,
-                                                          ws.W8, ws.levels, 4, _ptr(ws.corr.hi), _ptr(ws.corr.lo), CORR_LD,
+                                                          ws.W8, ws.levels, 4, _ptr(ws.corr.hi), _ptr(ws.corr.lo), CORR_LD, CORR_LS,
                                                           _stream()), "corr_lookup_split")
 
     def _update_iter(self, ws, pk, want_mask, want_delta):
@@ -248,7 +257,7 @@ class UmmaEngine(Engine):
         s = _stream()
         E = native
         # BasicMotionEncoder (update.py:89-97)
-        self.uconv(B, H, W, ws.corr.ptrs(), CORR_CH, CORR_LD, pk.convc1, E.EPI_RELU, out_split=ws.c1.ptrs(), ldo_split=256)
+        self.uconv(B, H, W, ws.corr.ptrs(), CORR_LD, CORR_LD, pk.convc1, E.EPI_RELU, out_split=ws.c1.ptrs(), ldo_split=256)
         self.uconv(B, H, W, ws.c1.ptrs(), 256, 256, pk.convc2, E.EPI_RELU, out_split=ws.corflo.ptrs(), ldo_split=256)
         native.check(self.L.rnc_conv_flow7x7_split_fwd(_ptr(ws.coords1), _ptr(pk.convf1[0]), _ptr(pk.convf1[1]), B, H, W, 128,
                                                        _ptr(ws.f1.hi), _ptr(ws.f1.lo), 128, s), "convf1")
@@ -285,8 +294,9 @@ class UmmaEngine(Engine):
         B, _, H, W = corr_nchw.shape
         tmp = torch.empty(B * H * W, CORR_CH, dtype=torch.float32, device=corr_nchw.device)
         native.check(self.L.rnc_nchw_to_cl(_ptr(corr_nchw), B, CORR_CH, H, W, _ptr(tmp), CORR_CH, 0, _stream()), "nchw_to_cl(corr)")
-        native.check(self.L.rnc_f32_to_split(_ptr(tmp), CORR_CH, CORR_CH, B * H * W, _ptr(ws.corr.hi), _ptr(ws.corr.lo), CORR_LD, 0,
-                                             _stream()), "f32_to_split(corr)")
+        for lvl in range(4):     # level l -> channels [l*88, l*88+81); the pads stay zero
+            native.check(self.L.rnc_f32_to_split(C.c_void_p(tmp.data_ptr() + 4 * 81 * lvl), CORR_CH, 81, B * H * W, _ptr(ws.corr.hi),
+                                                 _ptr(ws.corr.lo), CORR_LD, lvl * CORR_LS, _stream()), "f32_to_split(corr)")
 
     def net_nchw(self, ws):
         out = torch.empty(ws.B, 128, ws.H8, ws.W8, dtype=torch.float32, device=ws.h.device)

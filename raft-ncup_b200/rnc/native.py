@@ -10,7 +10,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librnc.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EPI_LINEAR, EPI_RELU, EPI_SIGMOID, EPI_GRU_ZR, EPI_GRU_Q, EPI_RELU_FLOW, EPI_RELU_ADD_RELU, EPI_TANH_RELU = range(8)
 CONV_NO_HALO, CONV_BASE_OFFSET = 1, 2
@@ -65,9 +65,9 @@ SIGNATURES = {
     "rnc_pyramid_offset": (C.c_size_t, [_i, _i, _i, _i, _i]),
     "rnc_fmap_prepare": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rnc_corr_lookup_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
-    "rnc_corr_lookup_split_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "rnc_corr_lookup_split_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "rnc_corr_lookup_umma_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
-    "rnc_corr_lookup_umma_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, C.c_size_t, _vp]),
+    "rnc_corr_lookup_umma_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, C.c_size_t, _vp]),
     "rnc_f32_to_f16": (_i, [_vp, _vp, C.c_size_t, _vp]),
     "rnc_conv2d_cl_fwd": (_i, [C.POINTER(ConvDesc), _vp]),
     "rnc_conv2d_umma_fwd": (_i, [C.POINTER(UmmaConvDesc), _vp]),

@@ -159,10 +159,10 @@ def resident_lookup(f1, f2, coords, lookup_mode):
     ws.corr.lo.fill_(0.0)
     eng.lookup_resident(ws)
     torch.cuda.synchronize()
-    out = (ws.corr.hi.float() + ws.corr.lo.float())
-    assert (ws.corr.hi[:, 324:] == 7.0).all()
+    out = (ws.corr.hi.float() + ws.corr.lo.float()).view(-1, 4, 88)        # padded per-level layout: 81 taps + 7 zero pads
+    assert (out[:, :, 81:] == 0).all() and (ws.corr.lo.view(-1, 4, 88)[:, :, 81:] == 0).all()
     flags = ws.lookup_flags.cpu() if lookup_mode == "umma" else None
-    return out[:, :324].view(B, H, W, 324).permute(0, 3, 1, 2).cpu(), flags
+    return out[:, :, :81].reshape(B, H, W, 324).permute(0, 3, 1, 2).cpu(), flags
 
 
 def fp16_tol(f1, f2):
