@@ -111,7 +111,9 @@ typedef enum {
   RNC_EPI_RELU_FLOW = 5,/* RELU, and channels [Cout, Cout+2) of out receive flow = coords1-coords0 (update.py:97);
                            aux0 = coords1 NCHW [B][2][H][W]                                     */
   RNC_EPI_RELU_ADD_RELU = 6, /* relu(res + relu(acc + bias)): residual block tail, extractor.py:48-55 (umma only) */
-  RNC_EPI_TANH_RELU = 7      /* ch < Cout/2: tanh (-> out_f32 and split), else relu (-> split): raft_nc_dbl.py:138-140 (umma only) */
+  RNC_EPI_TANH_RELU = 7,     /* ch < Cout/2: tanh (-> out_f32 and split), else relu (-> split): raft_nc_dbl.py:138-140 (umma only) */
+  RNC_EPI_FLOW_DELTA = 8     /* Cout = 2 (FlowHead.conv2, update.py:10,14): aux0 = coords1 NCHW [B][2][H][W] += (acc + bias)
+                                (raft_nc_dbl.py:157); out_f32, if given, receives delta_flow NCHW (umma only) */
 } rnc_epilogue;
 
 /* rnc_conv_umma_desc.flags */

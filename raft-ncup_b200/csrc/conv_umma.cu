@@ -250,6 +250,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
           }
           continue;
         }
+        if (epi == RNC_EPI_FLOW_DELTA) {
+          // FlowHead.conv2 + `coords1 = coords1 + delta_flow` (update.py:14, raft_nc_dbl.py:157); only channels 0,1 are real
+          const int HW = p.H * p.W;
+          const size_t i0 = static_cast<size_t>(b) * 2 * HW + y * p.W + x;
+          p.aux0[i0] += v[0];
+          p.aux0[i0 + HW] += v[1];
+          if (p.out_f32) { p.out_f32[i0] = v[0]; p.out_f32[i0 + HW] = v[1]; }
+          continue;
+        }
         bool want_f32 = p.out_f32 != nullptr;
         if (epi == RNC_EPI_GRU_Q) {
           const float4* zp = reinterpret_cast<const float4*>(p.aux0 + pix * p.ldaux + n);
@@ -424,6 +433,9 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
         if ((d.out_f32 && d.ldo_f32 < cpad) || (d.out_hi && d.ldo_split < cpad)) return RNC_ERR_BAD_SHAPE;
       }
       if (d.epilogue == RNC_EPI_TANH_RELU && (d.cout % 64) != 0) return RNC_ERR_BAD_SHAPE;
+      break;
+    case RNC_EPI_FLOW_DELTA:
+      if (!d.aux0 || d.cout != 2 || d.out_hi) return RNC_ERR_BAD_SHAPE;
       break;
     case RNC_EPI_GRU_ZR:
       if (!d.out_hi || !d.aux0 || !d.h || (d.cout % 64) != 0 || (d.ldaux & 3) || (d.ldh & 3)) return RNC_ERR_BAD_POINTER;

@@ -25,7 +25,13 @@ namespace lookup_umma {
 
 using namespace rnc::umma;
 
-constexpr int kThreads = 192;            // warp 0 TMA, warp 1 MMA + TMEM, warps 2-5 epilogue
+// kSplitEpi = true: 8 epilogue warps (two per TMEM lane group, splitting the slow window index i) and a 2-deep B ring;
+// false: 4 epilogue warps and a 3-deep B ring.  Measured on B200 (B=8, 55x128): 0.143 ms vs 0.139 ms per launch — the
+// kernel is bound by the TMA->MMA latency chain as much as by the epilogue, and shared memory cannot hold both the
+// second row buffer and the third stage.
+constexpr bool kSplitEpi = false;
+constexpr int kEpiWarps = kSplitEpi ? 8 : 4;
+constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA + TMEM, then the epilogue warps
 constexpr int kTY = 8, kTX = 16;         // query tile (level-0 pixels)
 constexpr int kD = 256;                  // feature channels
 constexpr int kKB = kD / 64;             // K blocks of 64 halves
@@ -37,13 +43,13 @@ __host__ __device__ constexpr int chunk_rows(int l) { return l < 2 ? 8 : 16; }
 __host__ __device__ constexpr int n_chunks(int l) { return l < 2 ? 3 : 1; }
 __host__ __device__ constexpr int box_h(int l) { return chunk_rows(l) * n_chunks(l); }
 constexpr int kChunks = 3 + 3 + 1 + 1;
-constexpr int kStages = 3;
+constexpr int kStages = kSplitEpi ? 2 : 3;
 constexpr int kATile = 128 * 64 * 2;     // 16 KB per K block
 constexpr int kBStage = 256 * 64 * 2;    // 32 KB: 256 positions x 64 halves
 constexpr int kLvlStride = 88;           // channels per level in the output row (81 taps + 7 zero pads): 16-byte groups
 constexpr int kSmemA = kKB * kATile;                         // 64 KB
 constexpr int kSmemB = kStages * kBStage;                    // 96 KB
-constexpr int kSmemScratch = 32 * 128 * 4;                   // 16 KB
+constexpr int kSmemScratch = (kSplitEpi ? 2 : 1) * 32 * 128 * 4;   // 16 KB row buffer per epilogue warp set
 constexpr int kSmemStage = 128 * 81 * 4;                     // 41.5 KB, [tap][pixel]
 constexpr int kSmemTotal = kSmemA + kSmemB + kSmemScratch + kSmemStage + 1024 + 512;
 
@@ -59,6 +65,127 @@ struct TileInfo {                      // shared: per-level union box of the til
   int bx0[kLevels], by0[kLevels], bx1[kLevels], by1[kLevels];
   int overflow;
 };
+
+struct EpiCtx {
+  const Params& p; const TileInfo* ti; float* scratch; float* stage; uint64_t* acc_full; uint64_t* acc_empty;
+  uint32_t tmem_base; int b, y0, x0, lg, ml, lane; bool valid; float cx, cy;
+};
+
+// Epilogue of one warp.  HALF selects the slow window index range this warp produces: 0 -> i in [0,5), 1 -> i in [5,9),
+// 2 -> all nine (single warp per lane group).
+template <int HALF>
+__device__ __forceinline__ void lookup_epilogue(const EpiCtx& c) {
+  constexpr int I0 = HALF == 1 ? 5 : 0, NI = HALF == 0 ? 5 : HALF == 1 ? 4 : 9;     // outputs i = I0 .. I0+NI-1 need g[I0 .. I0+NI]
+  constexpr int G0 = HALF == 1 ? 6 : 0, G1 = HALF == 0 ? 6 : kLvlStride / 8;           // 8-channel output groups this warp stores
+  const Params& p = c.p;
+  const int HW = p.H * p.W;
+  float* my_scratch = c.scratch + (HALF == 1 ? 32 * 128 : 0) + c.ml;   // [col][128] layout: thread-private column, conflict free
+  float* my_stage = c.stage + c.ml;                           // [tap][128] layout; the pair shares the pixel's column
+  int ch = 0;
+  float inv = 1.f;
+#pragma unroll 1
+  for (int l = 0; l < kLevels; ++l) {
+    const int Hl = p.H >> l, Wl = p.W >> l;
+    const float sx = c.cx * inv, sy = c.cy * inv;
+    inv *= 0.5f;
+    const float fx0 = floorf(sx), fy0 = floorf(sy);
+    const float ax = sx - fx0, ay = sy - fy0;
+    const int ix0 = static_cast<int>(fx0) - kR, iy0 = static_cast<int>(fy0) - kR;
+    const bool empty = ix0 + kG - 1 < 0 || ix0 > Wl - 1 || iy0 + kG - 1 < 0 || iy0 > Hl - 1;
+    const bool any = c.ti->bx1[l] >= c.ti->bx0[l];
+    const int ox = ix0 - (any ? c.ti->bx0[l] : 0), oy = iy0 - (any ? c.ti->by0[l] : 0);
+    const bool live = c.valid && !empty;
+    if (c.valid && empty) {
+      for (int k = I0 * kS; k < (I0 + NI) * kS; ++k) my_stage[k * 128] = 0.f;
+    }
+    const int bw = box_w(l), cr = chunk_rows(l);
+    float hprev[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) hprev[i] = 0.f;
+    // warp-uniform ranges of the box rows / columns that any pixel of this warp (2 tile rows) actually needs
+    const int row_lo = __reduce_min_sync(0xffffffffu, live ? oy : 0x7fffffff);
+    const int row_hi = __reduce_max_sync(0xffffffffu, live ? oy + kG - 1 : -1);
+    const int col_lo = __reduce_min_sync(0xffffffffu, live ? ox + I0 : 0x7fffffff);
+    const int col_hi = __reduce_max_sync(0xffffffffu, live ? ox + I0 + NI : -1);
+    // one box row: park the needed columns in the thread-private scratch column, gather the pixel's lattice values,
+    // interpolate in x, blend with the previous row in y -> NI outputs of window row j = cidx - 1
+    auto process_row = [&](const uint32_t* v, int ncols, int box_row) {
+#pragma unroll
+      for (int q = 0; q < 32; ++q)
+        if (q < ncols && q >= col_lo && q <= col_hi) my_scratch[q * 128] = __uint_as_float(v[q]);
+      const int cidx = box_row - oy;               // lattice row (y) of this pixel's window held by this box row
+      if (live && cidx >= 0 && cidx < kG) {
+        float g[NI + 1];
+#pragma unroll
+        for (int a = 0; a <= NI; ++a) g[a] = my_scratch[(ox + I0 + a) * 128];
+        float h[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) h[i] = (1.f - ax) * g[i] + ax * g[i + 1];
+        if (cidx >= 1) {
+          const int j = cidx - 1;
+#pragma unroll
+          for (int i = 0; i < NI; ++i) my_stage[((I0 + i) * kS + j) * 128] = ((1.f - ay) * hprev[i] + ay * h[i]) * p.scale;
+        }
+#pragma unroll
+        for (int i = 0; i < NI; ++i) hprev[i] = h[i];
+      }
+    };
+    for (int cc = 0; cc < n_chunks(l); ++cc, ++ch) {
+      const int buf = ch & 1, use = ch >> 1;
+      mbar_wait(&c.acc_full[buf], use & 1);
+      tcgen05_fence_after();
+      const int r0 = max(0, row_lo - cc * cr), r1 = min(cr - 1, row_hi - cc * cr);   // rows of this chunk the warp needs
+      const uint32_t tbase = c.tmem_base + (static_cast<uint32_t>(c.lg * 32) << 16) + buf * 256;
+      if (r0 <= r1) {
+        // software pipeline: the TMEM load of row r+1 is in flight while row r is processed
+        uint32_t va[32] = {}, vb[32] = {};
+        if (bw == 32) tmem_ld32_issue(tbase + r0 * 32, va); else tmem_ld16_issue(tbase + r0 * 16, va);
+        tmem_ld_wait32(va);
+        for (int r = r0; r <= r1; r += 2) {
+          if (r + 1 <= r1) { if (bw == 32) tmem_ld32_issue(tbase + (r + 1) * 32, vb); else tmem_ld16_issue(tbase + (r + 1) * 16, vb); }
+          process_row(va, bw, cc * cr + r);
+          tmem_ld_wait32(vb);
+          if (r + 1 <= r1) {
+            if (r + 2 <= r1) { if (bw == 32) tmem_ld32_issue(tbase + (r + 2) * 32, va); else tmem_ld16_issue(tbase + (r + 2) * 16, va); }
+            process_row(vb, bw, cc * cr + r + 1);
+            tmem_ld_wait32(va);
+          }
+        }
+      }
+      // all of this warp's reads of the TMEM buffer are complete
+      tcgen05_fence_before();
+      __syncwarp();
+      if (c.lane == 0) mbar_arrive(&c.acc_empty[buf]);
+    }
+    // ---- level done.  The level occupies kLvlStride (= 88, a multiple of 8) channels of the output row: 81 taps + 7 zero
+    // pads, so every group of 8 channels is one aligned 16-byte store per plane.  The pair splits the 11 groups; a 64-thread
+    // named barrier makes the partner's taps visible (and a second one protects them from the next level's writes).
+    if (HALF != 2) named_bar_sync(1 + c.lg, 64);
+    {
+      const int q = c.ml;
+      const int qy = c.y0 + (q >> 4), qx = c.x0 + (q & 15);
+      if (qy < p.H && qx < p.W) {
+        const size_t base = (static_cast<size_t>(c.b) * HW + qy * p.W + qx) * p.ldo + l * kLvlStride;
+#pragma unroll 1
+        for (int gq = G0; gq < G1; ++gq) {
+          __half2 hh[4], ll[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k0 = gq * 8 + 2 * j;
+            float v0 = k0 < kS * kS ? c.stage[k0 * 128 + q] : 0.f, v1 = k0 + 1 < kS * kS ? c.stage[(k0 + 1) * 128 + q] : 0.f;
+            v0 = fminf(fmaxf(v0, -65504.f), 65504.f); v1 = fminf(fmaxf(v1, -65504.f), 65504.f);
+            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+            hh[j] = __halves2half2(h0, h1);
+            ll[j] = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+          }
+          *reinterpret_cast<uint4*>(p.out_hi + base + gq * 8) = *reinterpret_cast<uint4*>(hh);
+          *reinterpret_cast<uint4*>(p.out_lo + base + gq * 8) = *reinterpret_cast<uint4*>(ll);
+        }
+      }
+    }
+    if (HALF != 2) named_bar_sync(1 + c.lg, 64);
+  }
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_constant__ CUtensorMap mL0,
@@ -134,7 +261,7 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
   if (threadIdx.x == 0) {
     mbar_init(a_full, 1);
     for (int s = 0; s < kStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -190,110 +317,11 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
     }
   } else {
     // ------------------------------------------------------------------ epilogue: gather + bilinear blend + store
-    float* my_scratch = scratch + ml;                // [col][128] layout: thread-private column, conflict free
-    float* my_stage = stage + ml;                    // [channel][128] layout, thread-private column
-    int ch = 0;
-    float inv = 1.f;
-#pragma unroll 1
-    for (int l = 0; l < kLevels; ++l) {
-      const int Hl = p.H >> l, Wl = p.W >> l;
-      const float sx = cx * inv, sy = cy * inv;
-      inv *= 0.5f;
-      const float fx0 = floorf(sx), fy0 = floorf(sy);
-      const float ax = sx - fx0, ay = sy - fy0;
-      const int ix0 = static_cast<int>(fx0) - kR, iy0 = static_cast<int>(fy0) - kR;
-      const bool empty = ix0 + kG - 1 < 0 || ix0 > Wl - 1 || iy0 + kG - 1 < 0 || iy0 > Hl - 1;
-      const bool any = ti->bx1[l] >= ti->bx0[l];
-      const int ox = ix0 - (any ? ti->bx0[l] : 0), oy = iy0 - (any ? ti->by0[l] : 0);
-      const bool live = valid && !empty;
-      if (valid && empty) {
-        for (int k = 0; k < kS * kS; ++k) my_stage[k * 128] = 0.f;
-      }
-      const int bw = box_w(l), cr = chunk_rows(l);
-      float hprev[kS];
-#pragma unroll
-      for (int i = 0; i < kS; ++i) hprev[i] = 0.f;
-      // warp-uniform ranges of the box rows / columns that any pixel of this warp (2 tile rows) actually needs
-      const int row_lo = __reduce_min_sync(0xffffffffu, live ? oy : 0x7fffffff);
-      const int row_hi = __reduce_max_sync(0xffffffffu, live ? oy + kG - 1 : -1);
-      const int col_lo = __reduce_min_sync(0xffffffffu, live ? ox : 0x7fffffff);
-      const int col_hi = __reduce_max_sync(0xffffffffu, live ? ox + kG - 1 : -1);
-      // one box row: park the needed columns in the thread-private scratch column, gather the pixel's 10 lattice values,
-      // interpolate in x, blend with the previous row in y -> 9 outputs of window row j = cidx - 1
-      auto process_row = [&](const uint32_t* v, int ncols, int box_row) {
-#pragma unroll
-        for (int q = 0; q < 32; ++q)
-          if (q < ncols && q >= col_lo && q <= col_hi) my_scratch[q * 128] = __uint_as_float(v[q]);
-        const int cidx = box_row - oy;               // lattice row (y) of this pixel's window held by this box row
-        if (live && cidx >= 0 && cidx < kG) {
-          float g[kG];
-#pragma unroll
-          for (int a = 0; a < kG; ++a) g[a] = my_scratch[(ox + a) * 128];
-          float h[kS];
-#pragma unroll
-          for (int i = 0; i < kS; ++i) h[i] = (1.f - ax) * g[i] + ax * g[i + 1];
-          if (cidx >= 1) {
-            const int j = cidx - 1;
-#pragma unroll
-            for (int i = 0; i < kS; ++i) my_stage[(i * kS + j) * 128] = ((1.f - ay) * hprev[i] + ay * h[i]) * p.scale;
-          }
-#pragma unroll
-          for (int i = 0; i < kS; ++i) hprev[i] = h[i];
-        }
-      };
-      for (int c = 0; c < n_chunks(l); ++c, ++ch) {
-        const int buf = ch & 1, use = ch >> 1;
-        mbar_wait(&acc_full[buf], use & 1);
-        tcgen05_fence_after();
-        const int r0 = max(0, row_lo - c * cr), r1 = min(cr - 1, row_hi - c * cr);   // rows of this chunk the warp needs
-        const uint32_t tbase = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + buf * 256;
-        if (r0 <= r1) {
-          // software pipeline: the TMEM load of row r+1 is in flight while row r is processed
-          uint32_t va[32] = {}, vb[32] = {};
-          if (bw == 32) tmem_ld32_issue(tbase + r0 * 32, va); else tmem_ld16_issue(tbase + r0 * 16, va);
-          tmem_ld_wait32(va);
-          for (int r = r0; r <= r1; r += 2) {
-            if (r + 1 <= r1) { if (bw == 32) tmem_ld32_issue(tbase + (r + 1) * 32, vb); else tmem_ld16_issue(tbase + (r + 1) * 16, vb); }
-            process_row(va, bw, c * cr + r);
-            tmem_ld_wait32(vb);
-            if (r + 1 <= r1) {
-              if (r + 2 <= r1) { if (bw == 32) tmem_ld32_issue(tbase + (r + 2) * 32, va); else tmem_ld16_issue(tbase + (r + 2) * 16, va); }
-              process_row(vb, bw, c * cr + r + 1);
-              tmem_ld_wait32(va);
-            }
-          }
-        }
-        // all of this warp's reads of the TMEM buffer are complete (tcgen05.wait::ld inside tmem_ld*)
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
-      }
-      // ---- level done: coalesced write-out of 128 px x 81 taps as hi/lo halves
-      // The level occupies kLvlStride (= 88, a multiple of 8) channels of the output row: 81 taps + 7 zero pads, so
-      // every group of 8 channels is one aligned 16-byte store per plane.  Thread = pixel; staging is [channel][pixel].
-      {
-        const int q = ml;        // staging column is thread-private (written and read by the same thread): no barrier
-        const int qy = y0 + (q >> 4), qx = x0 + (q & 15);
-        if (qy < p.H && qx < p.W) {
-          const size_t base = (static_cast<size_t>(b) * HW + qy * p.W + qx) * p.ldo + l * kLvlStride;
-#pragma unroll 1
-          for (int gq = 0; gq < kLvlStride / 8; ++gq) {
-            __half2 hh[4], ll[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int k0 = gq * 8 + 2 * j;
-              float v0 = k0 < kS * kS ? stage[k0 * 128 + q] : 0.f, v1 = k0 + 1 < kS * kS ? stage[(k0 + 1) * 128 + q] : 0.f;
-              v0 = fminf(fmaxf(v0, -65504.f), 65504.f); v1 = fminf(fmaxf(v1, -65504.f), 65504.f);
-              const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-              hh[j] = __halves2half2(h0, h1);
-              ll[j] = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
-            }
-            *reinterpret_cast<uint4*>(p.out_hi + base + gq * 8) = *reinterpret_cast<uint4*>(hh);
-            *reinterpret_cast<uint4*>(p.out_lo + base + gq * 8) = *reinterpret_cast<uint4*>(ll);
-          }
-        }
-      }
-    }
+    // two warps per TMEM lane group share the pixels: half 0 produces the taps i = 0..4, half 1 the taps i = 5..8
+    EpiCtx c{p, ti, scratch, stage, acc_full, acc_empty, tmem_base, b, y0, x0, lg, ml, lane, valid, cx, cy};
+    if (!kSplitEpi) lookup_epilogue<2>(c);
+    else if (warp - 2 < 4) lookup_epilogue<0>(c);
+    else lookup_epilogue<1>(c);
   }
 
   tcgen05_fence_before();

@@ -78,7 +78,7 @@ class PackedUpdateUmma:
         self.zr2 = UmmaWeights(cat([g.convz2.weight, g.convr2.weight], 0), cat([g.convz2.bias, g.convr2.bias], 0), [HX_LD])
         self.q2 = UmmaWeights(g.convq2.weight, g.convq2.bias, [128, 256])
         self.fh1 = UmmaWeights(fh.conv1.weight, fh.conv1.bias, [128])
-        self.fh2 = (pack_thin(fh.conv2.weight), fh.conv2.bias.detach().float().contiguous())
+        self.fh2 = UmmaWeights(fh.conv2.weight, fh.conv2.bias, [256])      # Cout = 2 padded to a 32-wide N tile
         self.has_mask = len(ub.mask) > 0
         if self.has_mask:
             self.m0 = UmmaWeights(ub.mask[0].weight, ub.mask[0].bias, [128])
@@ -127,7 +127,7 @@ class UmmaWorkspace:
         self.rh = SplitBuf(M, 128, device)
         self.h = torch.zeros(M, 128, **f)            # fp32 master copy of the GRU state
         self.z = torch.empty(M, 128, **f)
-        self.fh = torch.empty(M, 256, **f)
+        self.fh = SplitBuf(M, 256, device)
         self.tmp = torch.empty(M, 256, **f)
         self.coords1 = torch.empty(B, 2, H8, W8, **f)
         self.delta = torch.empty(B, 2, H8, W8, **f)
@@ -272,9 +272,9 @@ class UmmaEngine(Engine):
             self.uconv(B, H, W, ws.rh.ptrs(), 128, 128, q, E.EPI_GRU_Q, in1=ws.hx.ptrs(128), c1=256, ld1=HX_LD,
                        out_split=ws.hx.ptrs(), ldo_split=HX_LD, h=hp, ldh=128, aux0=ws.z.data_ptr(), ldaux=128)
         # FlowHead (update.py:13-14) + coords1 += delta (raft_nc_dbl.py:157)
-        self.uconv(B, H, W, ws.hx.ptrs(), 128, HX_LD, pk.fh1, E.EPI_RELU, out_f32=ws.fh.data_ptr(), ldo_f32=256)
-        native.check(self.L.rnc_flow_head2_fwd(_ptr(ws.fh), 256, 256, _ptr(pk.fh2[0]), _ptr(pk.fh2[1]), B, H, W,
-                                               _ptr(ws.delta) if want_delta else C.c_void_p(0), _ptr(ws.coords1), s), "flow_head2")
+        self.uconv(B, H, W, ws.hx.ptrs(), 128, HX_LD, pk.fh1, E.EPI_RELU, out_split=ws.fh.ptrs(), ldo_split=256)
+        self.uconv(B, H, W, ws.fh.ptrs(), 256, 256, pk.fh2, E.EPI_FLOW_DELTA, aux0=ws.coords1.data_ptr(),
+                   out_f32=ws.delta.data_ptr() if want_delta else 0)
         if want_mask:
             self.uconv(B, H, W, ws.hx.ptrs(), 128, HX_LD, pk.m0, E.EPI_RELU, out_split=ws.mh.ptrs(), ldo_split=256)
             self.uconv(B, H, W, ws.mh.ptrs(), 256, 256, pk.m2, E.EPI_LINEAR, out_f32=ws.mask.data_ptr(), ldo_f32=576)

@@ -12,7 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librnc.so")
 ABI_VERSION = 3
 
-EPI_LINEAR, EPI_RELU, EPI_SIGMOID, EPI_GRU_ZR, EPI_GRU_Q, EPI_RELU_FLOW, EPI_RELU_ADD_RELU, EPI_TANH_RELU = range(8)
+(EPI_LINEAR, EPI_RELU, EPI_SIGMOID, EPI_GRU_ZR, EPI_GRU_Q, EPI_RELU_FLOW, EPI_RELU_ADD_RELU, EPI_TANH_RELU,
+ EPI_FLOW_DELTA) = range(9)
 CONV_NO_HALO, CONV_BASE_OFFSET = 1, 2
 
 _vp, _i, _f = C.c_void_p, C.c_int, C.c_float
