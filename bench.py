@@ -28,6 +28,17 @@ import torch  # noqa: E402
 H_IMG, W_IMG, ITERS, BATCH = 436, 1024, 32, 8
 K2_BYTES_PER_PAIR_ITER = 25_891_840      # fmap1 + coords + out + fmap2 pyramid, fp32
 K4_BYTES_PER_PAIR_CALL = 3_886_080       # flow_lr + conf read, 2x64xP fp32 written
+# same formula at the storage width the tensor-core lookup uses: fp16 fmap1/fmap2 pyramid, fp32 coords, 2 x fp16 outputs
+K2_STORAGE_BYTES_PER_PAIR_ITER = 2 * 7040 * 256 + 8 * 7040 + 4 * 7040 * 324 + 2 * 256 * 9280
+
+
+def ncu_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full summary of this round."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(kernel_key, {}).get("dram_bytes_per_launch")
+    return None
 METRIC = "image-pairs/sec @ 1024x436, 32 iters"
 
 
@@ -227,10 +238,13 @@ def run_native(args, rank, world, local_rank):
                 "d2h_bytes_per_step": int(out_lo.numel() + out_up.numel()) * 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "corr_lookup_tile_kernel (fused corr lookup, K2)", "bound": "hbm", "achieved": k2_gbs, "peak": peak,
-                     "unit": "GB/s", "frac": k2_gbs / peak, "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": k2_bytes, "avg_launch_ms": k2_ms,
-                     "launches_timed": len(prof.get("corr_lookup", []))},
+        "roofline": {"kernel": "corr_lookup_umma_kernel (tcgen05 fused corr lookup, K2; + exact fallback launch)", "bound": "hbm",
+                     "achieved": k2_gbs, "peak": peak, "unit": "GB/s", "frac": k2_gbs / peak, "traffic": ncu_traffic("corr_lookup"),
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": k2_bytes,
+                     "algorithmic_bytes_note": "SURVEY §8d contract figure (fp32 storage: 25,891,840 B/pair-iter); at the storage "
+                                               "width actually used (fp16 features, 4 B hi/lo outputs) one launch moves "
+                                               f"{K2_STORAGE_BYTES_PER_PAIR_ITER * args.batch} B",
+                     "avg_launch_ms": k2_ms, "launches_timed": len(prof.get("corr_lookup", []))},
         "roofline_ncup": {"kernel": "ncup_fused_kernel (K4)", "bound": "hbm", "achieved": k4_gbs, "peak": peak, "unit": "GB/s",
                           "frac": k4_gbs / peak, "avg_launch_ms": k4_ms,
                           "algorithmic_bytes_per_launch": K4_BYTES_PER_PAIR_CALL * args.batch},

@@ -382,8 +382,11 @@ static int launch(const CUtensorMap* maps, Params& p, cudaStream_t stream) {
   using C = Cfg<BN>;
   // ring depths: A double buffered, B as deep as fits ~200 KB
   const int a_stage = 2 * p.a_plane;
+  // ring depths within ~208 KB: both rings hide the same TMA latency, so deepen A (up to 4) while B keeps >= 3 stages
+  const int budget = 208 * 1024, b_stage = 2 * C::kBTile;
   p.SA = 2;
-  int sb = (200 * 1024 - p.SA * a_stage) / (2 * C::kBTile);
+  while (p.SA < kMaxSA && budget - (p.SA + 1) * a_stage >= 3 * b_stage) ++p.SA;
+  int sb = (budget - p.SA * a_stage) / b_stage;
   p.SB = sb > kMaxSB ? kMaxSB : sb < 2 ? 2 : sb;
   const int smem = p.SA * a_stage + p.SB * 2 * C::kBTile + 1024 + 512;
   static unsigned long long done = 0;

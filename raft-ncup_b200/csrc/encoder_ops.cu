@@ -12,21 +12,23 @@
 namespace rnc {
 
 // ---------------------------------------------------------------- stem: 7x7 stride-2 conv on the raw image
-constexpr int ST_TX = 16, ST_TY = 8;                 // output tile: 128 px = 64 pixel pairs x 4 channel groups = 256 threads
+constexpr int ST_TX = 32, ST_TY = 8;                 // output tile: 256 px = 64 pixel quads x 4 channel groups = 256 threads
 constexpr int ST_IN_W = ST_TX * 2 + 5, ST_IN_H = ST_TY * 2 + 5;
+constexpr int ST_PW = ST_IN_W + 1;                   // patch row pitch
+constexpr int ST_SMEM = (3 * ST_IN_H * ST_PW + 147 * 64) * 4;   // 17.6 KB patch + 37.6 KB weights (dynamic: > 48 KB)
 
-// weight layout: [147 = (c*7+ky)*7+kx][64]; each thread: 1 output pixel x 64 channels would need 64 accumulators and
-// a weight broadcast per FMA; instead: thread = (pixel pair, 16-channel group): 4 groups x 128 pixel-pairs... keep it
-// simple and register-friendly: thread computes 2 horizontally adjacent pixels x 16 channels.
+// weight layout [147 = (c*7+ky)*7+kx][64].  Thread = (4 horizontally adjacent output pixels, 16-channel group): per
+// (channel, filter row) the 13 input values of the quad are loaded once and every weight float4 feeds 16 FMAs.
 __global__ void __launch_bounds__(256)
 stem_conv7x7s2_kernel(const float* __restrict__ img, const float* __restrict__ weight, const float* __restrict__ bias,
                       int N, int Hin, int Win, int Ho, int Wo, int relu, float* __restrict__ out_f32,
                       __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
-  __shared__ float patch[3][ST_IN_H][ST_IN_W + 1];
-  __shared__ __align__(16) float wsm[147][64];
+  extern __shared__ __align__(16) float st_smem[];
+  float* wsm = st_smem;                                // [147][64]
+  float* patch = st_smem + 147 * 64;                   // [3][ST_IN_H][ST_PW]
   const int n = blockIdx.z, oy0 = blockIdx.y * ST_TY, ox0 = blockIdx.x * ST_TX;
   const int tid = threadIdx.x;
-  for (int i = tid; i < 147 * 64; i += 256) wsm[i >> 6][i & 63] = weight[i];
+  for (int i = tid; i < 147 * 64 / 4; i += 256) reinterpret_cast<float4*>(wsm)[i] = reinterpret_cast<const float4*>(weight)[i];
   const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
   for (int i = tid; i < 3 * ST_IN_H * ST_IN_W; i += 256) {
     const int c = i / (ST_IN_H * ST_IN_W), r = i % (ST_IN_H * ST_IN_W);
@@ -34,36 +36,44 @@ stem_conv7x7s2_kernel(const float* __restrict__ img, const float* __restrict__ w
     const int y = iy0 + py, x = ix0 + px;
     float v = 0.f;                                     // zero padding applies to the NORMALISED image
     if (y >= 0 && y < Hin && x >= 0 && x < Win) v = 2.f * (img[((size_t)(n * 3 + c) * Hin + y) * Win + x] / 255.0f) - 1.0f;
-    patch[c][py][px] = v;
+    patch[(c * ST_IN_H + py) * ST_PW + px] = v;
   }
   __syncthreads();
-  // 128 pixels = 64 pairs; 256 threads = 64 pairs x 4 channel groups of 16
-  const int cg = tid & 3, pair = tid >> 2;
-  const int ty = pair / (ST_TX / 2), tx = (pair % (ST_TX / 2)) * 2;
-  float acc[2][16];
+  const int cg = tid & 3, quad = tid >> 2;
+  const int ty = quad / (ST_TX / 4), tx = (quad % (ST_TX / 4)) * 4;
+  float acc[4][16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) { acc[0][j] = bias[cg * 16 + j]; acc[1][j] = acc[0][j]; }
+  for (int j = 0; j < 16; ++j) {
+    const float bv = bias[cg * 16 + j];
+    acc[0][j] = bv; acc[1][j] = bv; acc[2][j] = bv; acc[3][j] = bv;
+  }
   for (int c = 0; c < 3; ++c)
     for (int ky = 0; ky < 7; ++ky) {
-      const float* prow = &patch[c][ty * 2 + ky][tx * 2];
+      const float* prow = &patch[(c * ST_IN_H + ty * 2 + ky) * ST_PW + tx * 2];
+      float a[13];
+#pragma unroll
+      for (int i = 0; i < 13; ++i) a[i] = prow[i];
 #pragma unroll
       for (int kx = 0; kx < 7; ++kx) {
-        const float a0 = prow[kx], a1 = prow[kx + 2];
-        const float4* w4 = reinterpret_cast<const float4*>(&wsm[(c * 7 + ky) * 7 + kx][cg * 16]);
+        const float4* w4 = reinterpret_cast<const float4*>(&wsm[((c * 7 + ky) * 7 + kx) * 64 + cg * 16]);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 w = w4[q];
-          acc[0][4 * q + 0] = fmaf(a0, w.x, acc[0][4 * q + 0]); acc[1][4 * q + 0] = fmaf(a1, w.x, acc[1][4 * q + 0]);
-          acc[0][4 * q + 1] = fmaf(a0, w.y, acc[0][4 * q + 1]); acc[1][4 * q + 1] = fmaf(a1, w.y, acc[1][4 * q + 1]);
-          acc[0][4 * q + 2] = fmaf(a0, w.z, acc[0][4 * q + 2]); acc[1][4 * q + 2] = fmaf(a1, w.z, acc[1][4 * q + 2]);
-          acc[0][4 * q + 3] = fmaf(a0, w.w, acc[0][4 * q + 3]); acc[1][4 * q + 3] = fmaf(a1, w.w, acc[1][4 * q + 3]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float av = a[2 * i + kx];
+            acc[i][4 * q + 0] = fmaf(av, w.x, acc[i][4 * q + 0]);
+            acc[i][4 * q + 1] = fmaf(av, w.y, acc[i][4 * q + 1]);
+            acc[i][4 * q + 2] = fmaf(av, w.z, acc[i][4 * q + 2]);
+            acc[i][4 * q + 3] = fmaf(av, w.w, acc[i][4 * q + 3]);
+          }
         }
       }
     }
   const int oy = oy0 + ty;
   if (oy >= Ho) return;
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 4; ++i) {
     const int ox = ox0 + tx + i;
     if (ox >= Wo) continue;
     const size_t base = (((size_t)n * Ho + oy) * Wo + ox) * 64 + cg * 16;
@@ -75,13 +85,18 @@ stem_conv7x7s2_kernel(const float* __restrict__ img, const float* __restrict__ w
       for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(out_f32 + base)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     }
     if (out_hi) {
+      __half2 hh[8], ll[8];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float vc = fminf(fmaxf(v[j], -65504.f), 65504.f);
-        const __half h = __float2half_rn(vc);
-        out_hi[base + j] = h;
-        out_lo[base + j] = __float2half_rn(vc - __half2float(h));
+      for (int j = 0; j < 8; ++j) {
+        const float v0 = fminf(fmaxf(v[2 * j], -65504.f), 65504.f), v1 = fminf(fmaxf(v[2 * j + 1], -65504.f), 65504.f);
+        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+        hh[j] = __halves2half2(h0, h1);
+        ll[j] = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
       }
+      reinterpret_cast<uint4*>(out_hi + base)[0] = reinterpret_cast<uint4*>(hh)[0];
+      reinterpret_cast<uint4*>(out_hi + base)[1] = reinterpret_cast<uint4*>(hh)[1];
+      reinterpret_cast<uint4*>(out_lo + base)[0] = reinterpret_cast<uint4*>(ll)[0];
+      reinterpret_cast<uint4*>(out_lo + base)[1] = reinterpret_cast<uint4*>(ll)[1];
     }
   }
 }
@@ -222,10 +237,12 @@ int rnc_stem_conv7x7s2_fwd(const float* img, const float* weight, const float* b
                            float* out_f32, void* out_hi, void* out_lo, void* stream) {
   if (N <= 0 || Hin <= 0 || Win <= 0) return RNC_ERR_BAD_SHAPE;
   if (!img || !weight || !bias || (!out_f32 && !out_hi) || (out_hi && !out_lo)) return RNC_ERR_BAD_POINTER;
-  if ((out_f32 && !aligned16(out_f32))) return RNC_ERR_BAD_POINTER;
+  if ((out_f32 && !aligned16(out_f32)) || (out_hi && (!aligned16(out_hi) || !aligned16(out_lo))) || !aligned16(weight)) return RNC_ERR_BAD_POINTER;
   const int Ho = (Hin + 1) / 2, Wo = (Win + 1) / 2;            // floor((H + 6 - 7)/2) + 1
   dim3 grid((Wo + ST_TX - 1) / ST_TX, (Ho + ST_TY - 1) / ST_TY, N);
-  stem_conv7x7s2_kernel<<<grid, 256, 0, as_stream(stream)>>>(img, weight, bias, N, Hin, Win, Ho, Wo, relu, out_f32,
+  static unsigned long long done = 0;
+  if (int st = ensure_dyn_smem(stem_conv7x7s2_kernel, ST_SMEM, &done)) return st;
+  stem_conv7x7s2_kernel<<<grid, 256, ST_SMEM, as_stream(stream)>>>(img, weight, bias, N, Hin, Win, Ho, Wo, relu, out_f32,
                                                             static_cast<__half*>(out_hi), static_cast<__half*>(out_lo));
   return after_launch();
 }
