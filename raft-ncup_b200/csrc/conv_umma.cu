@@ -113,7 +113,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // The whole warp runs the loop so that addresses / coordinates stay in uniform registers (UTMALDG and UTCHMMA take
+    // uniform operands; a loop under `if (lane == 0)` forces an R2UR chain in front of every issue); one elected lane issues.
+    {
       int a_it = 0, b_it = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int tile = item / p.ntn, n0 = (item - tile * p.ntn) * BN;
@@ -128,28 +130,34 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
             const int sa = a_it % p.SA, pa = (a_it / p.SA) & 1;
             ++a_it;
             mbar_wait(&a_empty[sa], pa ^ 1);
-            mbar_expect_tx(&a_full[sa], a_stage);
             const bool seg0 = cb < p.nblk0;
             const int c = (seg0 ? cb : cb - p.nblk0) * kBK;
-            tma_load_4d(sA + sa * a_stage, seg0 ? &mA0h : &mA1h, &a_full[sa], c, cx, cy, b);
-            tma_load_4d(sA + sa * a_stage + p.a_plane, seg0 ? &mA0l : &mA1l, &a_full[sa], c, cx, cy, b);
+            if (elect_one()) {
+              mbar_expect_tx(&a_full[sa], a_stage);
+              tma_load_4d(sA + sa * a_stage, seg0 ? &mA0h : &mA1h, &a_full[sa], c, cx, cy, b);
+              tma_load_4d(sA + sa * a_stage + p.a_plane, seg0 ? &mA0l : &mA1l, &a_full[sa], c, cx, cy, b);
+            }
+            __syncwarp();
             for (int t = 0; t < T; ++t) {
               const int tap = p.mode == MODE_TAP ? g : p.mode == MODE_ROWHALO ? g * p.kw + t : t;
               const int sb = b_it % p.SB, pb = (b_it / p.SB) & 1;
               ++b_it;
               mbar_wait(&b_empty[sb], pb ^ 1);
-              mbar_expect_tx(&b_full[sb], 2 * C::kBTile);
               const int kcol = (tap * p.nblk + cb) * kBK;
-              tma_load_2d(sB + sb * 2 * C::kBTile, &mBh, &b_full[sb], kcol, n0);
-              tma_load_2d(sB + sb * 2 * C::kBTile + C::kBTile, &mBl, &b_full[sb], kcol, n0);
+              if (elect_one()) {
+                mbar_expect_tx(&b_full[sb], 2 * C::kBTile);
+                tma_load_2d(sB + sb * 2 * C::kBTile, &mBh, &b_full[sb], kcol, n0);
+                tma_load_2d(sB + sb * 2 * C::kBTile + C::kBTile, &mBl, &b_full[sb], kcol, n0);
+              }
+              __syncwarp();
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
+    {
       const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(kBM >> 4) << 24);
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
       const int shift_rows = p.mode == MODE_ROWHALO ? 1 : p.mode == MODE_COLHALO ? p.TW : 0;
@@ -175,18 +183,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
               const uint64_t al = p.use_base_offset ? smem_desc_sw128_shift(ar + p.a_plane) : smem_desc_sw128(ar + p.a_plane);
               const uint32_t br = b_base + sb * 2 * C::kBTile;
               const uint64_t bh = smem_desc_sw128(br), bl = smem_desc_sw128(br + C::kBTile);
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < kBK / 16; ++k) {
-                umma_f16(d_main, ah + 2 * k, bh + 2 * k, idesc, acc);
-                umma_f16(d_corr, ah + 2 * k, bl + 2 * k, idesc, acc);
-                acc = 1;
-                umma_f16(d_corr, al + 2 * k, bh + 2 * k, idesc, 1);
+                for (int k = 0; k < kBK / 16; ++k) {
+                  umma_f16(d_main, ah + 2 * k, bh + 2 * k, idesc, k == 0 ? acc : 1u);
+                  umma_f16(d_corr, ah + 2 * k, bl + 2 * k, idesc, k == 0 ? acc : 1u);
+                  umma_f16(d_corr, al + 2 * k, bh + 2 * k, idesc, 1);
+                }
+                umma_commit(&b_empty[sb]);
               }
-              umma_commit(&b_empty[sb]);
+              __syncwarp();
+              acc = 1;
             }
-            umma_commit(&a_empty[sa]);
+            if (elect_one()) umma_commit(&a_empty[sa]);
+            __syncwarp();
           }
-        umma_commit(&acc_full[buf]);
+        if (elect_one()) umma_commit(&acc_full[buf]);
+        __syncwarp();
       }
     }
   } else {
@@ -378,7 +391,7 @@ static int sm_count() {
 }
 
 template <int BN>
-static int launch(const CUtensorMap* maps, Params& p, cudaStream_t stream) {
+static int launch(const CUtensorMap* maps, Params& p, cudaStream_t stream, int max_sa, int max_sb) {
   using C = Cfg<BN>;
   // ring depths: A double buffered, B as deep as fits ~200 KB
   const int a_stage = 2 * p.a_plane;
@@ -388,6 +401,8 @@ static int launch(const CUtensorMap* maps, Params& p, cudaStream_t stream) {
   while (p.SA < kMaxSA && budget - (p.SA + 1) * a_stage >= 3 * b_stage) ++p.SA;
   int sb = (budget - p.SA * a_stage) / b_stage;
   p.SB = sb > kMaxSB ? kMaxSB : sb < 2 ? 2 : sb;
+  if (max_sa > 0 && p.SA > max_sa) p.SA = max_sa;      // debug knobs (rnc_conv_umma_desc.flags bits 8-15)
+  if (max_sb > 0 && p.SB > max_sb) p.SB = max_sb;
   const int smem = p.SA * a_stage + p.SB * 2 * C::kBTile + 1024 + 512;
   static unsigned long long done = 0;
   if (int st = ensure_dyn_smem(conv_umma_kernel<BN>, 227 * 1024, &done)) return st;
@@ -495,10 +510,10 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
 
   cudaStream_t s = as_stream(stream);
   switch (bn) {
-    case 32: return launch<32>(maps, p, s);
-    case 64: return launch<64>(maps, p, s);
-    case 128: return launch<128>(maps, p, s);
-    case 192: return launch<192>(maps, p, s);
-    default: return launch<256>(maps, p, s);
+    case 32: return launch<32>(maps, p, s, (d.flags >> 8) & 15, (d.flags >> 12) & 15);
+    case 64: return launch<64>(maps, p, s, (d.flags >> 8) & 15, (d.flags >> 12) & 15);
+    case 128: return launch<128>(maps, p, s, (d.flags >> 8) & 15, (d.flags >> 12) & 15);
+    case 192: return launch<192>(maps, p, s, (d.flags >> 8) & 15, (d.flags >> 12) & 15);
+    default: return launch<256>(maps, p, s, (d.flags >> 8) & 15, (d.flags >> 12) & 15);
   }
 }
