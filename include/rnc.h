@@ -212,6 +212,11 @@ int rnc_coords_init(float* coords1, const float* flow_init, int B, int H, int W,
 /* flow = coords1 - grid  -> NCHW [B][2][H][W]  (raft_nc_dbl.py:152,170). */
 int rnc_coords_to_flow(const float* coords1, float* flow, int B, int H, int W, void* stream);
 
+/* Warm start: forward_interpolate (core/utils/utils.py:28-56; evaluate.py:38-40): push every pixel along its flow,
+ * keep samples landing strictly inside the image, give each grid point the flow of its nearest kept sample
+ * (scipy griddata 'nearest', fill 0).  flow, out: NCHW [B][2][H][W]. */
+int rnc_forward_interpolate_fwd(const float* flow, int B, int H, int W, float* out, void* stream);
+
 /* Layout plumbing between the reference's NCHW tensors and the resident CL buffers. */
 int rnc_nchw_to_cl(const float* src, int B, int C, int H, int W, float* dst, int ldd, int ch_off, void* stream);
 int rnc_cl_to_nchw(const float* src, int lds, int ch_off, int B, int C, int H, int W, float* dst, void* stream);

@@ -346,6 +346,23 @@ def raft_forward(sd, image1, image2, iters=12, model="raft_nc_dbl", flow_init=No
     return coords1 - coords0, flow_up, ups
 
 
+def forward_interpolate(flow):
+    """core/utils/utils.py:28-56 — push pixels along the flow, keep samples strictly inside the image, nearest-sample
+    interpolation back onto the grid (scipy griddata 'nearest', fill 0).  flow: [2,H,W] tensor; returns a [2,H,W] tensor."""
+    import numpy as np
+    from scipy import interpolate
+    f = flow.detach().cpu().numpy()
+    dx, dy = f[0], f[1]
+    ht, wd = dx.shape
+    x0, y0 = np.meshgrid(np.arange(wd), np.arange(ht))
+    x1, y1 = (x0 + dx).reshape(-1), (y0 + dy).reshape(-1)
+    dxr, dyr = dx.reshape(-1), dy.reshape(-1)
+    ok = (x1 > 0) & (x1 < wd) & (y1 > 0) & (y1 < ht)
+    fx = interpolate.griddata((x1[ok], y1[ok]), dxr[ok], (x0, y0), method="nearest", fill_value=0)
+    fy = interpolate.griddata((x1[ok], y1[ok]), dyr[ok], (x0, y0), method="nearest", fill_value=0)
+    return torch.from_numpy(np.stack([fx, fy], 0)).float()
+
+
 def sequence_loss(flow_preds, flow_gt, valid, gamma=0.8, max_flow=400.0):
     """train.py:46-71 — gamma-weighted L1 over all predictions; invalid pixels count in the mean's denominator."""
     n = len(flow_preds)

@@ -1,5 +1,7 @@
-"""Drop-in for `core/utils/utils.py`: InputPadder, coords_grid, upflow8, bilinear_sampler (host-side helpers the
-evaluation loops call around the model, evaluate.py:125-129)."""
+"""Drop-in for `core/utils/utils.py`: InputPadder, forward_interpolate, coords_grid, upflow8 — the host-side helpers the
+evaluation loops call around the model (evaluate.py:38-40, 125-129)."""
+import ctypes as C
+
 import torch
 import torch.nn.functional as F
 
@@ -23,6 +25,24 @@ class InputPadder:
     def unpad(self, x):
         l, r, t, b = self._pad
         return x[..., t:x.shape[-2] - b, l:x.shape[-1] - r]
+
+
+def forward_interpolate(flow):
+    """utils.py:28-56 — warm-start initialisation for the next frame: flow [2,H,W] (or [B,2,H,W]) on a CUDA device.
+    The reference round-trips through scipy on the CPU; this runs librnc's exact nearest-sample kernel on the GPU and
+    returns a tensor on the input's device (the reference returns a CPU tensor that its caller moves back with .cuda())."""
+    from rnc import native
+    from rnc.engine import _require_cuda
+    _require_cuda(flow)
+    squeeze = flow.dim() == 3
+    f = (flow[None] if squeeze else flow).detach().float().contiguous()
+    B, two, H, W = f.shape
+    if two != 2:
+        raise ValueError("flow must be [2,H,W] or [B,2,H,W]")
+    out = torch.empty_like(f)
+    native.check(native.lib().rnc_forward_interpolate_fwd(C.c_void_p(f.data_ptr()), B, H, W, C.c_void_p(out.data_ptr()),
+                                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)), "forward_interpolate")
+    return out[0] if squeeze else out
 
 
 def coords_grid(batch, ht, wd):
