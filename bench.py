@@ -210,6 +210,18 @@ def run_native(args, rank, world, local_rank):
     launches = native.launch_count()
     prof, eng.profile = eng.profile, None
     ms_e2e, _ = timed(step_e2e, args.steps)
+    # the lookup kernel alone (in the timed region convf1 runs underneath it on a side stream): 32 back-to-back launches
+    iso_ms = None
+    if hasattr(eng, "lookup_resident"):
+        ws = next(iter(eng._ws.values()))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(ITERS):
+            eng.lookup_resident(ws)
+        e1.record()
+        torch.cuda.synchronize()
+        iso_ms = e0.elapsed_time(e1) / ITERS
     clocks = sampler.stop() if rank == 0 else None
 
     pairs = world * args.batch * args.steps
@@ -244,7 +256,11 @@ def run_native(args, rank, world, local_rank):
                      "algorithmic_bytes_note": "SURVEY §8d contract figure (fp32 storage: 25,891,840 B/pair-iter); at the storage "
                                                "width actually used (fp16 features, 4 B hi/lo outputs) one launch moves "
                                                f"{K2_STORAGE_BYTES_PER_PAIR_ITER * args.batch} B",
-                     "avg_launch_ms": k2_ms, "launches_timed": len(prof.get("corr_lookup", []))},
+                     "avg_launch_ms": k2_ms, "launches_timed": len(prof.get("corr_lookup", [])),
+                     "isolated": {"avg_launch_ms": iso_ms, "achieved": (k2_bytes / (iso_ms * 1e-3) / 1e9) if iso_ms else None,
+                                  "frac": (k2_bytes / (iso_ms * 1e-3) / 1e9 / peak) if iso_ms else None,
+                                  "note": "same kernel, 32 back-to-back launches with nothing co-scheduled; in the timed region "
+                                          "the CUDA-core convf1 kernel shares the SMs with it on a side stream"}},
         "roofline_ncup": {"kernel": "ncup_fused_kernel (K4)", "bound": "hbm", "achieved": k4_gbs, "peak": peak, "unit": "GB/s",
                           "frac": k4_gbs / peak, "avg_launch_ms": k4_ms,
                           "algorithmic_bytes_per_launch": K4_BYTES_PER_PAIR_CALL * args.batch},

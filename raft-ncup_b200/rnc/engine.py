@@ -238,6 +238,9 @@ class Engine:
             native.check(self.L.rnc_corr_lookup_fwd(_ptr(ws.f1_cl), _ptr(ws.f2_pyr), _ptr(coords), ws.B, ws.D, ws.H8, ws.W8,
                                                     ws.levels, radius, _ptr(out), layout, ldo, _stream()), "corr_lookup")
 
+    def begin_iter(self, ws, pk):
+        """Hook called before the lookup of every iteration (the tensor-core engine forks independent work here)."""
+
     def lookup_resident(self, ws):
         """Per-iteration lookup at ws.coords1 into the resident corr buffer (CL fp32)."""
         self.lookup(ws, ws.coords1, ws.corr, 1, CORR_CH)

@@ -157,6 +157,8 @@ class UmmaEngine(Engine):
             raise ValueError(f"RNC_LOOKUP={self.lookup_mode!r}: expected 'umma' or 'ffma'")
         # RNC_CONV_FLAGS: bit 0 = one A tile per tap (no halo sharing), bit 1 = no descriptor base_offset (debug)
         self.conv_flags = int(os.environ.get("RNC_CONV_FLAGS", "0"))
+        self.fork_convf1 = os.environ.get("RNC_FORK", "1") != "0"
+        self._side = None
 
     def packed_update(self, ub):
         from .engine import _param_key
@@ -252,6 +254,23 @@ class UmmaEngine(Engine):
                                                           ws.W8, ws.levels, 4, _ptr(ws.corr.hi), _ptr(ws.corr.lo), CORR_LD, CORR_LS,
                                                           _stream()), "corr_lookup_split")
 
+    def _convf1(self, ws, pk):
+        native.check(self.L.rnc_conv_flow7x7_split_fwd(_ptr(ws.coords1), _ptr(pk.convf1[0]), _ptr(pk.convf1[1]), ws.B, ws.H8, ws.W8,
+                                                       128, _ptr(ws.f1.hi), _ptr(ws.f1.lo), 128, _stream()), "convf1")
+
+    def begin_iter(self, ws, pk):
+        """Fork: convf1 (7x7 on the flow, CUDA cores, ~1 KB of shared memory) depends only on coords1, so it runs on a side
+        stream underneath the tensor-core lookup / convc1 / convc2 CTAs that own the SMs; _update_iter joins before convf2."""
+        if not self.fork_convf1:
+            return
+        main = torch.cuda.current_stream()
+        if self._side is None or self._side.device != main.device:
+            self._side = torch.cuda.Stream(device=main.device)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            self._convf1(ws, pk)
+        ws.convf1_forked = True
+
     def _update_iter(self, ws, pk, want_mask, want_delta):
         B, H, W = ws.B, ws.H8, ws.W8
         s = _stream()
@@ -259,8 +278,11 @@ class UmmaEngine(Engine):
         # BasicMotionEncoder (update.py:89-97)
         self.uconv(B, H, W, ws.corr.ptrs(), CORR_LD, CORR_LD, pk.convc1, E.EPI_RELU, out_split=ws.c1.ptrs(), ldo_split=256)
         self.uconv(B, H, W, ws.c1.ptrs(), 256, 256, pk.convc2, E.EPI_RELU, out_split=ws.corflo.ptrs(), ldo_split=256)
-        native.check(self.L.rnc_conv_flow7x7_split_fwd(_ptr(ws.coords1), _ptr(pk.convf1[0]), _ptr(pk.convf1[1]), B, H, W, 128,
-                                                       _ptr(ws.f1.hi), _ptr(ws.f1.lo), 128, s), "convf1")
+        if getattr(ws, "convf1_forked", False):
+            torch.cuda.current_stream().wait_stream(self._side)       # join
+            ws.convf1_forked = False
+        else:
+            self._convf1(ws, pk)
         self.uconv(B, H, W, ws.f1.ptrs(), 128, 128, pk.convf2, E.EPI_RELU, out_split=ws.corflo.ptrs(192), ldo_split=256)
         self.uconv(B, H, W, ws.corflo.ptrs(), 256, 256, pk.conv, E.EPI_RELU_FLOW, out_split=ws.hx.ptrs(256), ldo_split=HX_LD,
                    aux0=ws.coords1.data_ptr())
