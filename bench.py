@@ -168,12 +168,33 @@ def run_native(args, rank, world, local_rank):
         with torch.no_grad():
             return model(d1, d2, iters=ITERS, test_mode=True)
 
+    # e2e: every step copies ITS inputs from pinned host memory and reads ITS flows back, inside the timed region.  Like any
+    # input pipeline, the H2D copy of step i+1 is issued on a copy stream while step i computes (double-buffered staging).
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [(torch.empty_like(d1), torch.empty_like(d2), torch.cuda.Event()) for _ in range(2)]
+    state = {"i": 0, "primed": False}
+
+    def prefetch(slot):
+        a, b, ev = stage[slot]
+        copy_stream.wait_stream(torch.cuda.current_stream())      # the slot's previous consumer has finished
+        with torch.cuda.stream(copy_stream):
+            a.copy_(h1, non_blocking=True)
+            b.copy_(h2, non_blocking=True)
+            ev.record(copy_stream)
+
     def step_e2e():
         with torch.no_grad():
-            a, b = h1.to(dev, non_blocking=True), h2.to(dev, non_blocking=True)
+            i = state["i"]
+            if not state["primed"]:
+                prefetch(i & 1)
+                state["primed"] = True
+            a, b, ev = stage[i & 1]
+            torch.cuda.current_stream().wait_event(ev)
+            prefetch((i + 1) & 1)                                    # next step's inputs travel during this step's compute
             lo, up = model(a, b, iters=ITERS, test_mode=True)
             out_lo.copy_(lo, non_blocking=True)
             out_up.copy_(up, non_blocking=True)
+            state["i"] = i + 1
         return lo, up
 
     def timed(fn, steps):

@@ -11,8 +11,8 @@
 //
 // Epilogue (thread = pixel = TMEM lane): one box row (BW columns) at a time is read with tcgen05.ld, parked in a
 // thread-private column of shared memory (dynamic addressing), the 10 lattice values of the pixel's window row are read
-// back, interpolated in x, combined with the previous row in y -> 9 outputs (fixed j, i = 0..8) into a staging tile,
-// which is written out per level as coalesced hi/lo split halves (the tcgen05 convolutions' operand format).
+// back, interpolated in x, combined with the previous row in y -> 9 outputs (fixed j, i = 0..8) into a staging row,
+// which is written out per level as 16-byte groups of hi/lo split halves (the tcgen05 convolutions' operand format).
 //
 // Tiles whose windows do not fit the fixed boxes (incoherent flow) are flagged and recomputed by the exact CUDA-core
 // kernel (corr_lookup.cu), so the result never depends on the coherence assumption.
@@ -37,20 +37,26 @@ constexpr int kD = 256;                  // feature channels
 constexpr int kKB = kD / 64;             // K blocks of 64 halves
 constexpr int kLevels = 4;
 constexpr int kS = 9, kG = 10, kR = 4;
-// per-level box: width, rows per chunk, chunks   (widths/heights seen on the benchmark stimuli: 28x24, 19x17, 15x14, 13x12)
-__host__ __device__ constexpr int box_w(int l) { return l < 2 ? 32 : 16; }
-__host__ __device__ constexpr int chunk_rows(int l) { return l < 2 ? 8 : 16; }
-__host__ __device__ constexpr int n_chunks(int l) { return l < 2 ? 3 : 1; }
+// per-level box: width, rows per chunk, chunks   (union boxes seen on the benchmark stimuli at iteration 31: 28x24, 19x17,
+// 15x14, 13x12; anything larger is handled by the exact fallback kernel)
+// boxes: 32x24, 24x20, 16x16, 16x14 positions = chunks of 256, 240, 256, 224 MMA columns
+__host__ __device__ constexpr int box_w(int l) { return l == 0 ? 32 : l == 1 ? 24 : 16; }
+__host__ __device__ constexpr int chunk_rows(int l) { return l == 0 ? 8 : l == 1 ? 10 : l == 2 ? 16 : 14; }
+__host__ __device__ constexpr int n_chunks(int l) { return l == 0 ? 3 : l == 1 ? 2 : 1; }
 __host__ __device__ constexpr int box_h(int l) { return chunk_rows(l) * n_chunks(l); }
-constexpr int kChunks = 3 + 3 + 1 + 1;
+__host__ __device__ constexpr int chunk_n(int l) { return box_w(l) * chunk_rows(l); }
 constexpr int kStages = kSplitEpi ? 2 : 3;
 constexpr int kATile = 128 * 64 * 2;     // 16 KB per K block
 constexpr int kBStage = 256 * 64 * 2;    // 32 KB: 256 positions x 64 halves
 constexpr int kLvlStride = 88;           // channels per level in the output row (81 taps + 7 zero pads): 16-byte groups
 constexpr int kSmemA = kKB * kATile;                         // 64 KB
 constexpr int kSmemB = kStages * kBStage;                    // 96 KB
-constexpr int kSmemScratch = (kSplitEpi ? 2 : 1) * 32 * 128 * 4;   // 16 KB row buffer per epilogue warp set
-constexpr int kSmemStage = 128 * 81 * 4;                     // 41.5 KB, [tap][pixel]
+// Epilogue buffers are pixel-major with 16-byte aligned rows, so a thread moves its data with 128-bit accesses:
+//   scratch [pixel][36]: one box row of the accumulator; 36 = 4*9 -> the 8 lanes of a quarter warp hit 8 distinct bank quads
+//   stage   [pixel][84]: the level's 81 taps (+3);       84 = 4*21 -> same property
+constexpr int kScrStride = 36, kStgStride = 84;
+constexpr int kSmemScratch = (kSplitEpi ? 2 : 1) * 128 * kScrStride * 4;   // 18 KB row buffer per epilogue warp set
+constexpr int kSmemStage = 128 * kStgStride * 4;             // 42 KB
 constexpr int kSmemTotal = kSmemA + kSmemB + kSmemScratch + kSmemStage + 1024 + 512;
 
 struct Params {
@@ -61,10 +67,19 @@ struct Params {
   float scale;
 };
 
-struct TileInfo {                      // shared: per-level union box of the tile
-  int bx0[kLevels], by0[kLevels], bx1[kLevels], by1[kLevels];
-  int overflow;
+struct TileInfo {                      // shared: per-level origin of the tile's union box (0,0 when no window is live)
+  int bx0[kLevels], by0[kLevels];
+  int overflow, pad[7];
 };
+
+// Window origin of one pixel at one level (shared by the producer's box computation and the epilogue's gather).
+__device__ __forceinline__ bool window_origin(float cx, float cy, float inv, int Hl, int Wl, int& ix0, int& iy0) {
+  ix0 = static_cast<int>(floorf(cx * inv)) - kR;
+  iy0 = static_cast<int>(floorf(cy * inv)) - kR;
+  return !(ix0 + kG - 1 < 0 || ix0 > Wl - 1 || iy0 + kG - 1 < 0 || iy0 > Hl - 1);   // false: window fully outside -> zeros
+}
+
+__device__ __forceinline__ float clamp_coord(float v) { return fminf(fmaxf(v, -1.0e6f), 1.0e6f); }
 
 struct EpiCtx {
   const Params& p; const TileInfo* ti; float* scratch; float* stage; uint64_t* acc_full; uint64_t* acc_empty;
@@ -74,29 +89,26 @@ struct EpiCtx {
 // Epilogue of one warp.  HALF selects the slow window index range this warp produces: 0 -> i in [0,5), 1 -> i in [5,9),
 // 2 -> all nine (single warp per lane group).
 template <int HALF>
-__device__ __forceinline__ void lookup_epilogue(const EpiCtx& c) {
+__device__ __forceinline__ void lookup_epilogue(const EpiCtx& c, int& ch) {
   constexpr int I0 = HALF == 1 ? 5 : 0, NI = HALF == 0 ? 5 : HALF == 1 ? 4 : 9;     // outputs i = I0 .. I0+NI-1 need g[I0 .. I0+NI]
   constexpr int G0 = HALF == 1 ? 6 : 0, G1 = HALF == 0 ? 6 : kLvlStride / 8;           // 8-channel output groups this warp stores
   const Params& p = c.p;
   const int HW = p.H * p.W;
-  float* my_scratch = c.scratch + (HALF == 1 ? 32 * 128 : 0) + c.ml;   // [col][128] layout: thread-private column, conflict free
-  float* my_stage = c.stage + c.ml;                           // [tap][128] layout; the pair shares the pixel's column
-  int ch = 0;
+  float* my_scratch = c.scratch + (HALF == 1 ? 128 * kScrStride : 0) + c.ml * kScrStride;   // thread-private row
+  float* my_stage = c.stage + c.ml * kStgStride;              // the pair shares the pixel's row
   float inv = 1.f;
 #pragma unroll 1
   for (int l = 0; l < kLevels; ++l) {
     const int Hl = p.H >> l, Wl = p.W >> l;
     const float sx = c.cx * inv, sy = c.cy * inv;
+    const float ax = sx - floorf(sx), ay = sy - floorf(sy);
+    int ix0, iy0;
+    const bool empty = !window_origin(c.cx, c.cy, inv, Hl, Wl, ix0, iy0);
     inv *= 0.5f;
-    const float fx0 = floorf(sx), fy0 = floorf(sy);
-    const float ax = sx - fx0, ay = sy - fy0;
-    const int ix0 = static_cast<int>(fx0) - kR, iy0 = static_cast<int>(fy0) - kR;
-    const bool empty = ix0 + kG - 1 < 0 || ix0 > Wl - 1 || iy0 + kG - 1 < 0 || iy0 > Hl - 1;
-    const bool any = c.ti->bx1[l] >= c.ti->bx0[l];
-    const int ox = ix0 - (any ? c.ti->bx0[l] : 0), oy = iy0 - (any ? c.ti->by0[l] : 0);
+    const int ox = ix0 - c.ti->bx0[l], oy = iy0 - c.ti->by0[l];
     const bool live = c.valid && !empty;
     if (c.valid && empty) {
-      for (int k = I0 * kS; k < (I0 + NI) * kS; ++k) my_stage[k * 128] = 0.f;
+      for (int k = I0 * kS; k < (I0 + NI) * kS; ++k) my_stage[k] = 0.f;
     }
     const int bw = box_w(l), cr = chunk_rows(l);
     float hprev[NI];
@@ -109,22 +121,25 @@ __device__ __forceinline__ void lookup_epilogue(const EpiCtx& c) {
     const int col_hi = __reduce_max_sync(0xffffffffu, live ? ox + I0 + NI : -1);
     // one box row: park the needed columns in the thread-private scratch column, gather the pixel's lattice values,
     // interpolate in x, blend with the previous row in y -> NI outputs of window row j = cidx - 1
+    const float wx1 = ax * p.scale, wx0 = p.scale - wx1, wy0 = 1.f - ay;   // the 1/sqrt(D) scale rides on the x weights
     auto process_row = [&](const uint32_t* v, int ncols, int box_row) {
 #pragma unroll
-      for (int q = 0; q < 32; ++q)
-        if (q < ncols && q >= col_lo && q <= col_hi) my_scratch[q * 128] = __uint_as_float(v[q]);
+      for (int g4 = 0; g4 < 8; ++g4)        // warp-uniform guards: only the column quads some pixel of the warp reads
+        if (4 * g4 < ncols && 4 * g4 + 3 >= col_lo && 4 * g4 <= col_hi)
+          *reinterpret_cast<uint4*>(my_scratch + 4 * g4) = make_uint4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
       const int cidx = box_row - oy;               // lattice row (y) of this pixel's window held by this box row
       if (live && cidx >= 0 && cidx < kG) {
+        const float* gp = my_scratch + ox + I0;
         float g[NI + 1];
 #pragma unroll
-        for (int a = 0; a <= NI; ++a) g[a] = my_scratch[(ox + I0 + a) * 128];
+        for (int a = 0; a <= NI; ++a) g[a] = gp[a];
         float h[NI];
 #pragma unroll
-        for (int i = 0; i < NI; ++i) h[i] = (1.f - ax) * g[i] + ax * g[i + 1];
+        for (int i = 0; i < NI; ++i) h[i] = wx0 * g[i] + wx1 * g[i + 1];
         if (cidx >= 1) {
           const int j = cidx - 1;
 #pragma unroll
-          for (int i = 0; i < NI; ++i) my_stage[((I0 + i) * kS + j) * 128] = ((1.f - ay) * hprev[i] + ay * h[i]) * p.scale;
+          for (int i = 0; i < NI; ++i) my_stage[(I0 + i) * kS + j] = wy0 * hprev[i] + ay * h[i];
         }
 #pragma unroll
         for (int i = 0; i < NI; ++i) hprev[i] = h[i];
@@ -139,14 +154,14 @@ __device__ __forceinline__ void lookup_epilogue(const EpiCtx& c) {
       if (r0 <= r1) {
         // software pipeline: the TMEM load of row r+1 is in flight while row r is processed
         uint32_t va[32] = {}, vb[32] = {};
-        if (bw == 32) tmem_ld32_issue(tbase + r0 * 32, va); else tmem_ld16_issue(tbase + r0 * 16, va);
+        if (bw > 16) tmem_ld32_issue(tbase + r0 * bw, va); else tmem_ld16_issue(tbase + r0 * bw, va);
         tmem_ld_wait32(va);
         for (int r = r0; r <= r1; r += 2) {
-          if (r + 1 <= r1) { if (bw == 32) tmem_ld32_issue(tbase + (r + 1) * 32, vb); else tmem_ld16_issue(tbase + (r + 1) * 16, vb); }
+          if (r + 1 <= r1) { if (bw > 16) tmem_ld32_issue(tbase + (r + 1) * bw, vb); else tmem_ld16_issue(tbase + (r + 1) * bw, vb); }
           process_row(va, bw, cc * cr + r);
           tmem_ld_wait32(vb);
           if (r + 1 <= r1) {
-            if (r + 2 <= r1) { if (bw == 32) tmem_ld32_issue(tbase + (r + 2) * 32, va); else tmem_ld16_issue(tbase + (r + 2) * 16, va); }
+            if (r + 2 <= r1) { if (bw > 16) tmem_ld32_issue(tbase + (r + 2) * bw, va); else tmem_ld16_issue(tbase + (r + 2) * bw, va); }
             process_row(vb, bw, cc * cr + r + 1);
             tmem_ld_wait32(va);
           }
@@ -166,17 +181,25 @@ __device__ __forceinline__ void lookup_epilogue(const EpiCtx& c) {
       const int qy = c.y0 + (q >> 4), qx = c.x0 + (q & 15);
       if (qy < p.H && qx < p.W) {
         const size_t base = (static_cast<size_t>(c.b) * HW + qy * p.W + qx) * p.ldo + l * kLvlStride;
+        const float* srow = c.stage + q * kStgStride;
 #pragma unroll 1
         for (int gq = G0; gq < G1; ++gq) {
+          float v[8];
+          if (gq < 10) {
+            const float4 a = *reinterpret_cast<const float4*>(srow + gq * 8), bq = *reinterpret_cast<const float4*>(srow + gq * 8 + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = bq.x; v[5] = bq.y; v[6] = bq.z; v[7] = bq.w;
+          } else {                                   // taps 80 + the 7 zero pads
+            v[0] = srow[80];
+#pragma unroll
+            for (int j = 1; j < 8; ++j) v[j] = 0.f;
+          }
           __half2 hh[4], ll[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int k0 = gq * 8 + 2 * j;
-            float v0 = k0 < kS * kS ? c.stage[k0 * 128 + q] : 0.f, v1 = k0 + 1 < kS * kS ? c.stage[(k0 + 1) * 128 + q] : 0.f;
-            v0 = fminf(fmaxf(v0, -65504.f), 65504.f); v1 = fminf(fmaxf(v1, -65504.f), 65504.f);
-            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-            hh[j] = __halves2half2(h0, h1);
-            ll[j] = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+            const float v0 = fminf(fmaxf(v[2 * j], -65504.f), 65504.f), v1 = fminf(fmaxf(v[2 * j + 1], -65504.f), 65504.f);
+            hh[j] = __floats2half2_rn(v0, v1);
+            const float2 back = __half22float2(hh[j]);
+            ll[j] = __floats2half2_rn(v0 - back.x, v1 - back.y);
           }
           *reinterpret_cast<uint4*>(p.out_hi + base + gq * 8) = *reinterpret_cast<uint4*>(hh);
           *reinterpret_cast<uint4*>(p.out_lo + base + gq * 8) = *reinterpret_cast<uint4*>(ll);
@@ -187,6 +210,12 @@ __device__ __forceinline__ void lookup_epilogue(const EpiCtx& c) {
   }
 }
 
+// Persistent kernel: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The three roles run decoupled
+// through mbarrier rings, so the TMA loads and MMAs of tile n+1 overlap the gather/blend/store epilogue of tile n:
+//   warp 0      producer: loads the tile's coords, reduces the per-level union boxes, publishes them (ti ring, 2 slots),
+//               then streams A (per K block, as soon as the previous tile's last chunk released it) and the B chunks
+//   warp 1      MMA issuer; TMEM accumulators are double buffered across chunks and tiles
+//   warps 2..   epilogue
 __global__ void __launch_bounds__(kThreads, 1)
 corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_constant__ CUtensorMap mL0,
                         const __grid_constant__ CUtensorMap mL1, const __grid_constant__ CUtensorMap mL2,
@@ -198,70 +227,29 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
   float* scratch = reinterpret_cast<float*>(smem + kSmemA + kSmemB);
   float* stage = reinterpret_cast<float*>(smem + kSmemA + kSmemB + kSmemScratch);
   unsigned char* tail = smem + kSmemA + kSmemB + kSmemScratch + kSmemStage;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* b_full = a_full + 1;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);       // [kKB]
+  uint64_t* a_empty = a_full + kKB;                           // [kKB]
+  uint64_t* b_full = a_empty + kKB;
   uint64_t* b_empty = b_full + kStages;
   uint64_t* acc_full = b_empty + kStages;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  TileInfo* ti = reinterpret_cast<TileInfo*>(tmem_slot + 2);
+  uint64_t* ti_full = acc_empty + 2;                          // [2]
+  uint64_t* ti_empty = ti_full + 2;                           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ti_empty + 2);
+  TileInfo* ti = reinterpret_cast<TileInfo*>(tmem_slot + 2);  // [2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
   const int tpi = p.tiles_x * p.tiles_y;
-  const int b = tile / tpi, tr = tile - b * tpi;
-  const int y0 = (tr / p.tiles_x) * kTY, x0 = (tr % p.tiles_x) * kTX;
+  const int ntiles = p.B * tpi;
   const int HW = p.H * p.W;
 
-  // ---- per-pixel window origins (epilogue threads own one pixel each) and the tile's union boxes
-  const bool is_epi = warp >= 2;
-  const int lg = warp & 3, ml = lg * 32 + lane;
-  const int py = y0 + (ml >> 4), px = x0 + (ml & 15);
-  const bool valid = is_epi && py < p.H && px < p.W;
-  float cx = 0.f, cy = 0.f;
-  if (valid) {
-    cx = p.coords[(static_cast<size_t>(b) * 2 + 0) * HW + py * p.W + px];
-    cy = p.coords[(static_cast<size_t>(b) * 2 + 1) * HW + py * p.W + px];
-  }
-  cx = fminf(fmaxf(cx, -1.0e6f), 1.0e6f);
-  cy = fminf(fmaxf(cy, -1.0e6f), 1.0e6f);
-
-  if (threadIdx.x < kLevels) {
-    ti->bx0[threadIdx.x] = 0x7fffffff; ti->by0[threadIdx.x] = 0x7fffffff;
-    ti->bx1[threadIdx.x] = -0x7fffffff; ti->by1[threadIdx.x] = -0x7fffffff;
-    if (threadIdx.x == 0) ti->overflow = 0;
-  }
-  __syncthreads();
-  if (valid) {
-    float inv = 1.f;
-#pragma unroll
-    for (int l = 0; l < kLevels; ++l) {
-      const int Hl = p.H >> l, Wl = p.W >> l;
-      const int ix0 = static_cast<int>(floorf(cx * inv)) - kR, iy0 = static_cast<int>(floorf(cy * inv)) - kR;
-      inv *= 0.5f;
-      const bool empty = ix0 + kG - 1 < 0 || ix0 > Wl - 1 || iy0 + kG - 1 < 0 || iy0 > Hl - 1;   // window fully outside: zeros
-      if (!empty) {
-        atomicMin(&ti->bx0[l], ix0); atomicMin(&ti->by0[l], iy0);
-        atomicMax(&ti->bx1[l], ix0 + kG - 1); atomicMax(&ti->by1[l], iy0 + kG - 1);
-      }
-    }
-  }
-  __syncthreads();
   if (threadIdx.x == 0) {
-    int ov = 0;
-#pragma unroll
-    for (int l = 0; l < kLevels; ++l)
-      if (ti->bx1[l] >= ti->bx0[l] && (ti->bx1[l] - ti->bx0[l] + 1 > box_w(l) || ti->by1[l] - ti->by0[l] + 1 > box_h(l))) ov = 1;
-    ti->overflow = ov;
-    p.flags[tile] = ov;
-  }
-  __syncthreads();
-  if (ti->overflow) return;            // whole CTA: the exact kernel recomputes this tile
-
-  if (threadIdx.x == 0) {
-    mbar_init(a_full, 1);
+    for (int kb = 0; kb < kKB; ++kb) { mbar_init(&a_full[kb], 1); mbar_init(&a_empty[kb], 1); }
     for (int s = 0; s < kStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps);
+      mbar_init(&ti_full[i], 1); mbar_init(&ti_empty[i], kEpiWarps + 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -271,57 +259,157 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      mbar_expect_tx(a_full, kSmemA);
+    // ------------------------------------------------------------------ producer (warp-uniform loops, one elected lane issues)
+    // lane owns pixels lane, lane+32, lane+64, lane+96 of the tile for the box reduction
+    float pcx[4], pcy[4];
+    auto load_coords = [&](int tile, float (&ox)[4], float (&oy)[4]) {
+      const int b = tile / tpi, tr = tile - b * tpi;
+      const int y0 = (tr / p.tiles_x) * kTY, x0 = (tr % p.tiles_x) * kTX;
 #pragma unroll
-      for (int kb = 0; kb < kKB; ++kb) tma_load_4d(sA + kb * kATile, &mF1, a_full, kb * 64, x0, y0, b);
-      int it = 0;
+      for (int j = 0; j < 4; ++j) {
+        const int ml = lane + 32 * j, py = y0 + (ml >> 4), px = x0 + (ml & 15);
+        const bool v = py < p.H && px < p.W;
+        ox[j] = v ? clamp_coord(__ldg(p.coords + (static_cast<size_t>(b) * 2 + 0) * HW + py * p.W + px)) : __int_as_float(0x7fc00000);
+        oy[j] = v ? clamp_coord(__ldg(p.coords + (static_cast<size_t>(b) * 2 + 1) * HW + py * p.W + px)) : 0.f;
+      }
+    };
+    if (static_cast<int>(blockIdx.x) < ntiles) load_coords(blockIdx.x, pcx, pcy);
+    int it = 0, n = 0, nv = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+      const int b = tile / tpi, tr = tile - b * tpi;
+      const int y0 = (tr / p.tiles_x) * kTY, x0 = (tr % p.tiles_x) * kTX;
+      int bx0[kLevels], by0[kLevels];
+      int ov = 0;
+      {
+        float inv = 1.f;
+#pragma unroll
+        for (int l = 0; l < kLevels; ++l) {
+          int lx0 = 0x7fffffff, ly0 = 0x7fffffff, lx1 = -0x7fffffff, ly1 = -0x7fffffff;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            int ix0, iy0;
+            if (pcx[j] == pcx[j] && window_origin(pcx[j], pcy[j], inv, p.H >> l, p.W >> l, ix0, iy0)) {   // NaN marks a pixel outside the image
+              lx0 = min(lx0, ix0); ly0 = min(ly0, iy0); lx1 = max(lx1, ix0 + kG - 1); ly1 = max(ly1, iy0 + kG - 1);
+            }
+          }
+          inv *= 0.5f;
+          lx0 = __reduce_min_sync(0xffffffffu, lx0); ly0 = __reduce_min_sync(0xffffffffu, ly0);
+          lx1 = __reduce_max_sync(0xffffffffu, lx1); ly1 = __reduce_max_sync(0xffffffffu, ly1);
+          const bool any = lx1 >= lx0;
+          if (any && (lx1 - lx0 + 1 > box_w(l) || ly1 - ly0 + 1 > box_h(l))) ov = 1;
+          bx0[l] = any ? lx0 : 0; by0[l] = any ? ly0 : 0;
+        }
+      }
+      // the next tile's coords travel while this tile's loads are issued
+      if (tile + static_cast<int>(gridDim.x) < ntiles) load_coords(tile + gridDim.x, pcx, pcy);
+      const int slot = n & 1;
+      mbar_wait(&ti_empty[slot], ((n >> 1) & 1) ^ 1);
+      if (lane == 0) {
+#pragma unroll
+        for (int l = 0; l < kLevels; ++l) { ti[slot].bx0[l] = bx0[l]; ti[slot].by0[l] = by0[l]; }
+        ti[slot].overflow = ov;
+        p.flags[tile] = ov;
+        mbar_arrive(&ti_full[slot]);         // release: the tile record is visible to the waiters
+      }
+      __syncwarp();
+      if (ov) continue;                      // the exact kernel recomputes this tile
+#pragma unroll
+      for (int kb = 0; kb < kKB; ++kb) {
+        mbar_wait(&a_empty[kb], (nv & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&a_full[kb], kATile);
+          tma_load_4d(sA + kb * kATile, &mF1, &a_full[kb], kb * 64, x0, y0, b);
+        }
+        __syncwarp();
+      }
 #pragma unroll
       for (int l = 0; l < kLevels; ++l) {
         const CUtensorMap* map = l == 0 ? &mL0 : l == 1 ? &mL1 : l == 2 ? &mL2 : &mL3;
-        const bool any = ti->bx1[l] >= ti->bx0[l];
-        const int bx0 = any ? ti->bx0[l] : 0, by0 = any ? ti->by0[l] : 0;
         for (int c = 0; c < n_chunks(l); ++c)
           for (int kb = 0; kb < kKB; ++kb, ++it) {
             const int s = it % kStages, ph = (it / kStages) & 1;
             mbar_wait(&b_empty[s], ph ^ 1);
-            mbar_expect_tx(&b_full[s], kBStage);
-            tma_load_4d(sB + s * kBStage, map, &b_full[s], kb * 64, bx0, by0 + c * chunk_rows(l), b);
+            if (elect_one()) {
+              mbar_expect_tx(&b_full[s], chunk_n(l) * 128);
+              tma_load_4d(sB + s * kBStage, map, &b_full[s], kb * 64, bx0[l], by0[l] + c * chunk_rows(l), b);
+            }
+            __syncwarp();
           }
       }
+      ++nv;
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(256 >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
-      mbar_wait(a_full, 0);
-      tcgen05_fence_after();
-      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-      int it = 0;
-      for (int ch = 0; ch < kChunks; ++ch) {
-        const int buf = ch & 1, use = ch >> 1;
-        mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
-        tcgen05_fence_after();
-        for (int kb = 0; kb < kKB; ++kb, ++it) {
-          const int s = it % kStages, ph = (it / kStages) & 1;
-          mbar_wait(&b_full[s], ph);
-          tcgen05_fence_after();
-          const uint64_t ad = smem_desc_sw128(a_base + kb * kATile), bd = smem_desc_sw128(b_base + s * kBStage);
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loops, one elected lane issues)
+    const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+    int it = 0, ch = 0, n = 0, nv = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+      const int slot = n & 1;
+      mbar_wait(&ti_full[slot], (n >> 1) & 1);
+      const int ov = ti[slot].overflow;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ti_empty[slot]);
+      if (ov) continue;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tmem_base + buf * 256, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
-          umma_commit(&b_empty[s]);
+      for (int l = 0; l < kLevels; ++l) {
+        // instruction descriptor: D = F32, A = B = F16, K-major, N = positions of this level's chunk, M = 128
+        const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(chunk_n(l) >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+        for (int c = 0; c < n_chunks(l); ++c, ++ch) {
+          const bool first = l == 0 && c == 0, final = l == kLevels - 1 && c == n_chunks(l) - 1;
+          const int buf = ch & 1, use = ch >> 1;
+          mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
+          tcgen05_fence_after();
+          for (int kb = 0; kb < kKB; ++kb, ++it) {
+            const int s = it % kStages, ph = (it / kStages) & 1;
+            if (first) mbar_wait(&a_full[kb], nv & 1);
+            mbar_wait(&b_full[s], ph);
+            tcgen05_fence_after();
+            const uint64_t ad = smem_desc_sw128(a_base + kb * kATile), bd = smem_desc_sw128(b_base + s * kBStage);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16(tmem_base + buf * 256, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+              umma_commit(&b_empty[s]);
+              if (final) umma_commit(&a_empty[kb]);   // this K block of A is free for the next tile
+            }
+            __syncwarp();
+          }
+          if (elect_one()) umma_commit(&acc_full[buf]);
+          __syncwarp();
         }
-        umma_commit(&acc_full[buf]);
       }
+      ++nv;
     }
   } else {
     // ------------------------------------------------------------------ epilogue: gather + bilinear blend + store
-    // two warps per TMEM lane group share the pixels: half 0 produces the taps i = 0..4, half 1 the taps i = 5..8
-    EpiCtx c{p, ti, scratch, stage, acc_full, acc_empty, tmem_base, b, y0, x0, lg, ml, lane, valid, cx, cy};
-    if (!kSplitEpi) lookup_epilogue<2>(c);
-    else if (warp - 2 < 4) lookup_epilogue<0>(c);
-    else lookup_epilogue<1>(c);
+    // thread = pixel = TMEM lane; with kSplitEpi two warps per lane group share the pixels: half 0 produces the taps
+    // i = 0..4, half 1 the taps i = 5..8
+    const int lg = warp & 3, ml = lg * 32 + lane;
+    auto load_coord = [&](int tile, float& ox, float& oy, bool& v) {
+      const int b = tile / tpi, tr = tile - b * tpi;
+      const int py = (tr / p.tiles_x) * kTY + (ml >> 4), px = (tr % p.tiles_x) * kTX + (ml & 15);
+      v = py < p.H && px < p.W;
+      ox = v ? clamp_coord(__ldg(p.coords + (static_cast<size_t>(b) * 2 + 0) * HW + py * p.W + px)) : 0.f;
+      oy = v ? clamp_coord(__ldg(p.coords + (static_cast<size_t>(b) * 2 + 1) * HW + py * p.W + px)) : 0.f;
+    };
+    float cx = 0.f, cy = 0.f, ncx = 0.f, ncy = 0.f;
+    bool valid = false, nvalid = false;
+    if (static_cast<int>(blockIdx.x) < ntiles) load_coord(blockIdx.x, ncx, ncy, nvalid);
+    int ch = 0, n = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+      cx = ncx; cy = ncy; valid = nvalid;
+      if (tile + static_cast<int>(gridDim.x) < ntiles) load_coord(tile + gridDim.x, ncx, ncy, nvalid);
+      const int b = tile / tpi, tr = tile - b * tpi;
+      const int y0 = (tr / p.tiles_x) * kTY, x0 = (tr % p.tiles_x) * kTX;
+      const int slot = n & 1;
+      mbar_wait(&ti_full[slot], (n >> 1) & 1);
+      if (!ti[slot].overflow) {
+        EpiCtx c{p, &ti[slot], scratch, stage, acc_full, acc_empty, tmem_base, b, y0, x0, lg, ml, lane, valid, cx, cy};
+        if (!kSplitEpi) lookup_epilogue<2>(c, ch);
+        else if (warp - 2 < 4) lookup_epilogue<0>(c, ch);
+        else lookup_epilogue<1>(c, ch);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ti_empty[slot]);
+    }
   }
 
   tcgen05_fence_before();
@@ -361,6 +449,17 @@ extern "C" int rnc_f32_to_f16(const float* src, void* dst, size_t n, void* strea
 extern "C" size_t rnc_corr_lookup_umma_workspace_bytes(int B, int H, int W) {
   using namespace lookup_umma;
   return static_cast<size_t>(B) * ((H + kTY - 1) / kTY) * ((W + kTX - 1) / kTX) * sizeof(int);
+}
+
+static int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached = n;
+  }
+  return cached;
 }
 
 // defined in corr_lookup.cu: exact kernel restricted to flagged 8x16 tiles, split-halves output
@@ -403,7 +502,8 @@ extern "C" int rnc_corr_lookup_umma_fwd(const void* f1h_cl, const void* f2h_pyr,
   static unsigned long long done = 0;
   if (int st = ensure_dyn_smem(corr_lookup_umma_kernel, kSmemTotal, &done)) return st;
   const int ntiles = B * p.tiles_x * p.tiles_y;
-  corr_lookup_umma_kernel<<<ntiles, kThreads, kSmemTotal, as_stream(stream)>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  const int grid = ntiles < sm_count() ? ntiles : sm_count();   // persistent: one CTA per SM
+  corr_lookup_umma_kernel<<<grid, kThreads, kSmemTotal, as_stream(stream)>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
   if (int st = after_launch()) return st;
   // exact recomputation of the tiles the fixed boxes could not cover
   return rnc_corr_lookup_fallback_split(f1_cl, f2_pyr, coords, B, D, H, W, levels, out_hi, out_lo, ldo, lvl_stride, p.flags,
