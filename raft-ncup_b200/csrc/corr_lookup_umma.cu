@@ -18,6 +18,8 @@
 // kernel (corr_lookup.cu), so the result never depends on the coherence assumption.
 //
 // Precision: fmaps are rounded once to fp16 (fp32 accumulate): 2.4e-4 EPE after 32 iterations in SURVEY.md Appendix D.
+#include <type_traits>
+
 #include "umma_ptx.cuh"
 
 namespace rnc {
@@ -25,12 +27,9 @@ namespace lookup_umma {
 
 using namespace rnc::umma;
 
-// kSplitEpi = true: 8 epilogue warps (two per TMEM lane group, splitting the slow window index i) and a 2-deep B ring;
-// false: 4 epilogue warps and a 3-deep B ring.  Measured on B200 (B=8, 55x128): 0.143 ms vs 0.139 ms per launch — the
-// kernel is bound by the TMA->MMA latency chain as much as by the epilogue, and shared memory cannot hold both the
-// second row buffer and the third stage.
-constexpr bool kSplitEpi = false;
-constexpr int kEpiWarps = kSplitEpi ? 8 : 4;
+// One epilogue warp per TMEM lane group.  (A second warp per lane group splitting the slow window index i was measured
+// on B200 at 0.105 ms vs 0.106 ms per launch: it duplicates the accumulator-row parking, which is most of the work.)
+constexpr int kEpiWarps = 4;
 constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA + TMEM, then the epilogue warps
 constexpr int kTY = 8, kTX = 16;         // query tile (level-0 pixels)
 constexpr int kD = 256;                  // feature channels
@@ -45,17 +44,18 @@ __host__ __device__ constexpr int chunk_rows(int l) { return l == 0 ? 8 : l == 1
 __host__ __device__ constexpr int n_chunks(int l) { return l == 0 ? 3 : l == 1 ? 2 : 1; }
 __host__ __device__ constexpr int box_h(int l) { return chunk_rows(l) * n_chunks(l); }
 __host__ __device__ constexpr int chunk_n(int l) { return box_w(l) * chunk_rows(l); }
-constexpr int kStages = kSplitEpi ? 2 : 3;
+constexpr int kStages = 2;               // B ring (a third stage does not fit beside the two-row scratch and measures the same)
 constexpr int kATile = 128 * 64 * 2;     // 16 KB per K block
 constexpr int kBStage = 256 * 64 * 2;    // 32 KB: 256 positions x 64 halves
 constexpr int kLvlStride = 88;           // channels per level in the output row (81 taps + 7 zero pads): 16-byte groups
 constexpr int kSmemA = kKB * kATile;                         // 64 KB
 constexpr int kSmemB = kStages * kBStage;                    // 96 KB
 // Epilogue buffers are pixel-major with 16-byte aligned rows, so a thread moves its data with 128-bit accesses:
-//   scratch [pixel][36]: one box row of the accumulator; 36 = 4*9 -> the 8 lanes of a quarter warp hit 8 distinct bank quads
+//   scratch [pixel][68]: two box rows (32 words each) of the accumulator; 68 = 4*17 -> the 8 lanes of a quarter warp hit
+//                        8 distinct bank quads
 //   stage   [pixel][84]: the level's 81 taps (+3);       84 = 4*21 -> same property
-constexpr int kScrStride = 36, kStgStride = 84;
-constexpr int kSmemScratch = (kSplitEpi ? 2 : 1) * 128 * kScrStride * 4;   // 18 KB row buffer per epilogue warp set
+constexpr int kScrStride = 68, kStgStride = 84;
+constexpr int kSmemScratch = 128 * kScrStride * 4;           // 34 KB
 constexpr int kSmemStage = 128 * kStgStride * 4;             // 42 KB
 constexpr int kSmemTotal = kSmemA + kSmemB + kSmemScratch + kSmemStage + 1024 + 512;
 
@@ -86,16 +86,98 @@ struct EpiCtx {
   uint32_t tmem_base; int b, y0, x0, lg, ml, lane; bool valid; float cx, cy;
 };
 
-// Epilogue of one warp.  HALF selects the slow window index range this warp produces: 0 -> i in [0,5), 1 -> i in [5,9),
-// 2 -> all nine (single warp per lane group).
-template <int HALF>
+template <int BW>
+__device__ __forceinline__ void tmem_row_issue(uint32_t taddr, uint32_t* v) {
+  if (BW > 16) tmem_ld32_issue(taddr, v); else tmem_ld16_issue(taddr, v);
+}
+
+// Rows of one level (box width BW columns) for the warp's 32 pixels: two box rows per step, so that two independent
+// store -> gather -> interpolate chains are in flight for the single epilogue warp of each scheduler.
+template <int BW>
+__device__ __forceinline__ void lookup_level_rows(const EpiCtx& c, int& ch, int l, bool live, int ox, int oy, float ax, float ay) {
+  const Params& p = c.p;
+  const int cr = chunk_rows(l);
+  float* sc = c.scratch + c.ml * kScrStride;                  // thread-private: two box rows of 32 words
+  float* st = c.stage + c.ml * kStgStride;                    // thread-private: the level's 81 taps
+  const float wx1 = ax * p.scale, wx0 = p.scale - wx1, wy0 = 1.f - ay;   // the 1/sqrt(D) scale rides on the x weights
+  // warp-uniform range of box rows that any pixel of this warp (2 tile rows) actually needs
+  const int row_lo = __reduce_min_sync(0xffffffffu, live ? oy : 0x7fffffff);
+  const int row_hi = __reduce_max_sync(0xffffffffu, live ? oy + kG - 1 : -1);
+  float hprev[kS];
+#pragma unroll
+  for (int i = 0; i < kS; ++i) hprev[i] = 0.f;
+  const float* gp = sc + (live ? ox : 0);
+
+  // one step: box rows `row`, `row + 1` (TWO) are in the scratch; cidx = lattice row of the pixel's window held by `row`
+  auto step = [&](int row, auto two_tag) {
+    constexpr bool TWO = decltype(two_tag)::value;
+    const int cidx = row - oy;
+    float g0[kG], g1[kG], h0[kS], h1[kS];
+#pragma unroll
+    for (int a = 0; a < kG; ++a) g0[a] = gp[a];
+    if (TWO) {
+#pragma unroll
+      for (int a = 0; a < kG; ++a) g1[a] = gp[32 + a];
+    }
+#pragma unroll
+    for (int i = 0; i < kS; ++i) h0[i] = wx0 * g0[i] + wx1 * g0[i + 1];
+    if (TWO) {
+#pragma unroll
+      for (int i = 0; i < kS; ++i) h1[i] = wx0 * g1[i] + wx1 * g1[i + 1];
+    }
+    if (live && cidx >= 1 && cidx < kG) {
+#pragma unroll
+      for (int i = 0; i < kS; ++i) st[i * kS + cidx - 1] = wy0 * hprev[i] + ay * h0[i];
+    }
+    if (TWO && live && cidx >= 0 && cidx < kG - 1) {
+#pragma unroll
+      for (int i = 0; i < kS; ++i) st[i * kS + cidx] = wy0 * h0[i] + ay * h1[i];
+    }
+#pragma unroll
+    for (int i = 0; i < kS; ++i) hprev[i] = TWO ? h1[i] : h0[i];
+  };
+  auto park = [&](const uint32_t* v, int half) {
+#pragma unroll
+    for (int g4 = 0; g4 < BW / 4; ++g4)
+      *reinterpret_cast<uint4*>(sc + half * 32 + 4 * g4) = make_uint4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+  };
+
+  for (int cc = 0; cc < n_chunks(l); ++cc, ++ch) {
+    const int buf = ch & 1, use = ch >> 1;
+    mbar_wait(&c.acc_full[buf], use & 1);
+    tcgen05_fence_after();
+    const int r0 = max(0, row_lo - cc * cr), r1 = min(cr - 1, row_hi - cc * cr);   // rows of this chunk the warp needs
+    const uint32_t tbase = c.tmem_base + (static_cast<uint32_t>(c.lg * 32) << 16) + buf * 256;
+    if (r0 <= r1) {
+      // software pipeline: the TMEM loads of the next two rows are in flight while this pair is processed
+      uint32_t va[32] = {}, vb[32] = {};
+      tmem_row_issue<BW>(tbase + r0 * BW, va);
+      if (r0 + 1 <= r1) tmem_row_issue<BW>(tbase + (r0 + 1) * BW, vb);
+      tmem_ld_wait32(va);
+      tmem_ld_wait32(vb);
+      for (int r = r0; r <= r1; r += 2) {
+        const bool two = r + 1 <= r1, more = r + 2 <= r1;
+        park(va, 0);
+        if (two) park(vb, 1);
+        if (more) tmem_row_issue<BW>(tbase + (r + 2) * BW, va);
+        if (r + 3 <= r1) tmem_row_issue<BW>(tbase + (r + 3) * BW, vb);
+        if (two) step(cc * cr + r, std::true_type{}); else step(cc * cr + r, std::false_type{});
+        if (more) { tmem_ld_wait32(va); tmem_ld_wait32(vb); }
+      }
+    }
+    // all of this warp's reads of the TMEM buffer are complete
+    tcgen05_fence_before();
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(&c.acc_empty[buf]);
+  }
+}
+
+// Epilogue of one warp (thread = pixel = TMEM lane) for one tile: all levels, rows then write-out.
 __device__ __forceinline__ void lookup_epilogue(const EpiCtx& c, int& ch) {
-  constexpr int I0 = HALF == 1 ? 5 : 0, NI = HALF == 0 ? 5 : HALF == 1 ? 4 : 9;     // outputs i = I0 .. I0+NI-1 need g[I0 .. I0+NI]
-  constexpr int G0 = HALF == 1 ? 6 : 0, G1 = HALF == 0 ? 6 : kLvlStride / 8;           // 8-channel output groups this warp stores
   const Params& p = c.p;
   const int HW = p.H * p.W;
-  float* my_scratch = c.scratch + (HALF == 1 ? 128 * kScrStride : 0) + c.ml * kScrStride;   // thread-private row
-  float* my_stage = c.stage + c.ml * kStgStride;              // the pair shares the pixel's row
+  float* st = c.stage + c.ml * kStgStride;
+  const int qy = c.y0 + (c.ml >> 4), qx = c.x0 + (c.ml & 15);
   float inv = 1.f;
 #pragma unroll 1
   for (int l = 0; l < kLevels; ++l) {
@@ -108,105 +190,40 @@ __device__ __forceinline__ void lookup_epilogue(const EpiCtx& c, int& ch) {
     const int ox = ix0 - c.ti->bx0[l], oy = iy0 - c.ti->by0[l];
     const bool live = c.valid && !empty;
     if (c.valid && empty) {
-      for (int k = I0 * kS; k < (I0 + NI) * kS; ++k) my_stage[k] = 0.f;
+      for (int k = 0; k < kS * kS; ++k) st[k] = 0.f;
     }
-    const int bw = box_w(l), cr = chunk_rows(l);
-    float hprev[NI];
-#pragma unroll
-    for (int i = 0; i < NI; ++i) hprev[i] = 0.f;
-    // warp-uniform ranges of the box rows / columns that any pixel of this warp (2 tile rows) actually needs
-    const int row_lo = __reduce_min_sync(0xffffffffu, live ? oy : 0x7fffffff);
-    const int row_hi = __reduce_max_sync(0xffffffffu, live ? oy + kG - 1 : -1);
-    const int col_lo = __reduce_min_sync(0xffffffffu, live ? ox + I0 : 0x7fffffff);
-    const int col_hi = __reduce_max_sync(0xffffffffu, live ? ox + I0 + NI : -1);
-    // one box row: park the needed columns in the thread-private scratch column, gather the pixel's lattice values,
-    // interpolate in x, blend with the previous row in y -> NI outputs of window row j = cidx - 1
-    const float wx1 = ax * p.scale, wx0 = p.scale - wx1, wy0 = 1.f - ay;   // the 1/sqrt(D) scale rides on the x weights
-    auto process_row = [&](const uint32_t* v, int ncols, int box_row) {
-#pragma unroll
-      for (int g4 = 0; g4 < 8; ++g4)        // warp-uniform guards: only the column quads some pixel of the warp reads
-        if (4 * g4 < ncols && 4 * g4 + 3 >= col_lo && 4 * g4 <= col_hi)
-          *reinterpret_cast<uint4*>(my_scratch + 4 * g4) = make_uint4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
-      const int cidx = box_row - oy;               // lattice row (y) of this pixel's window held by this box row
-      if (live && cidx >= 0 && cidx < kG) {
-        const float* gp = my_scratch + ox + I0;
-        float g[NI + 1];
-#pragma unroll
-        for (int a = 0; a <= NI; ++a) g[a] = gp[a];
-        float h[NI];
-#pragma unroll
-        for (int i = 0; i < NI; ++i) h[i] = wx0 * g[i] + wx1 * g[i + 1];
-        if (cidx >= 1) {
-          const int j = cidx - 1;
-#pragma unroll
-          for (int i = 0; i < NI; ++i) my_stage[(I0 + i) * kS + j] = wy0 * hprev[i] + ay * h[i];
-        }
-#pragma unroll
-        for (int i = 0; i < NI; ++i) hprev[i] = h[i];
-      }
-    };
-    for (int cc = 0; cc < n_chunks(l); ++cc, ++ch) {
-      const int buf = ch & 1, use = ch >> 1;
-      mbar_wait(&c.acc_full[buf], use & 1);
-      tcgen05_fence_after();
-      const int r0 = max(0, row_lo - cc * cr), r1 = min(cr - 1, row_hi - cc * cr);   // rows of this chunk the warp needs
-      const uint32_t tbase = c.tmem_base + (static_cast<uint32_t>(c.lg * 32) << 16) + buf * 256;
-      if (r0 <= r1) {
-        // software pipeline: the TMEM load of row r+1 is in flight while row r is processed
-        uint32_t va[32] = {}, vb[32] = {};
-        if (bw > 16) tmem_ld32_issue(tbase + r0 * bw, va); else tmem_ld16_issue(tbase + r0 * bw, va);
-        tmem_ld_wait32(va);
-        for (int r = r0; r <= r1; r += 2) {
-          if (r + 1 <= r1) { if (bw > 16) tmem_ld32_issue(tbase + (r + 1) * bw, vb); else tmem_ld16_issue(tbase + (r + 1) * bw, vb); }
-          process_row(va, bw, cc * cr + r);
-          tmem_ld_wait32(vb);
-          if (r + 1 <= r1) {
-            if (r + 2 <= r1) { if (bw > 16) tmem_ld32_issue(tbase + (r + 2) * bw, va); else tmem_ld16_issue(tbase + (r + 2) * bw, va); }
-            process_row(vb, bw, cc * cr + r + 1);
-            tmem_ld_wait32(va);
-          }
-        }
-      }
-      // all of this warp's reads of the TMEM buffer are complete
-      tcgen05_fence_before();
-      __syncwarp();
-      if (c.lane == 0) mbar_arrive(&c.acc_empty[buf]);
-    }
+    if (l == 0) lookup_level_rows<box_w(0)>(c, ch, l, live, ox, oy, ax, ay);
+    else if (l == 1) lookup_level_rows<box_w(1)>(c, ch, l, live, ox, oy, ax, ay);
+    else lookup_level_rows<box_w(2)>(c, ch, l, live, ox, oy, ax, ay);
+    static_assert(box_w(2) == box_w(3), "levels 2 and 3 share the row code");
     // ---- level done.  The level occupies kLvlStride (= 88, a multiple of 8) channels of the output row: 81 taps + 7 zero
-    // pads, so every group of 8 channels is one aligned 16-byte store per plane.  The pair splits the 11 groups; a 64-thread
-    // named barrier makes the partner's taps visible (and a second one protects them from the next level's writes).
-    if (HALF != 2) named_bar_sync(1 + c.lg, 64);
-    {
-      const int q = c.ml;
-      const int qy = c.y0 + (q >> 4), qx = c.x0 + (q & 15);
-      if (qy < p.H && qx < p.W) {
-        const size_t base = (static_cast<size_t>(c.b) * HW + qy * p.W + qx) * p.ldo + l * kLvlStride;
-        const float* srow = c.stage + q * kStgStride;
-#pragma unroll 1
-        for (int gq = G0; gq < G1; ++gq) {
-          float v[8];
-          if (gq < 10) {
-            const float4 a = *reinterpret_cast<const float4*>(srow + gq * 8), bq = *reinterpret_cast<const float4*>(srow + gq * 8 + 4);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = bq.x; v[5] = bq.y; v[6] = bq.z; v[7] = bq.w;
-          } else {                                   // taps 80 + the 7 zero pads
-            v[0] = srow[80];
+    // pads, so every group of 8 channels is one aligned 16-byte store per plane.  Two groups per step (independent chains).
+    if (qy < p.H && qx < p.W) {
+      const size_t base = (static_cast<size_t>(c.b) * HW + qy * p.W + qx) * p.ldo + l * kLvlStride;
+      auto emit = [&](const float (&v)[8], int gq) {
+        __half2 hh[4], ll[4];
 #pragma unroll
-            for (int j = 1; j < 8; ++j) v[j] = 0.f;
-          }
-          __half2 hh[4], ll[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float v0 = fminf(fmaxf(v[2 * j], -65504.f), 65504.f), v1 = fminf(fmaxf(v[2 * j + 1], -65504.f), 65504.f);
-            hh[j] = __floats2half2_rn(v0, v1);
-            const float2 back = __half22float2(hh[j]);
-            ll[j] = __floats2half2_rn(v0 - back.x, v1 - back.y);
-          }
-          *reinterpret_cast<uint4*>(p.out_hi + base + gq * 8) = *reinterpret_cast<uint4*>(hh);
-          *reinterpret_cast<uint4*>(p.out_lo + base + gq * 8) = *reinterpret_cast<uint4*>(ll);
+        for (int j = 0; j < 4; ++j) {
+          const float v0 = fminf(fmaxf(v[2 * j], -65504.f), 65504.f), v1 = fminf(fmaxf(v[2 * j + 1], -65504.f), 65504.f);
+          hh[j] = __floats2half2_rn(v0, v1);
+          const float2 back = __half22float2(hh[j]);
+          ll[j] = __floats2half2_rn(v0 - back.x, v1 - back.y);
         }
+        *reinterpret_cast<uint4*>(p.out_hi + base + gq * 8) = *reinterpret_cast<uint4*>(hh);
+        *reinterpret_cast<uint4*>(p.out_lo + base + gq * 8) = *reinterpret_cast<uint4*>(ll);
+      };
+#pragma unroll 1
+      for (int gq = 0; gq < 10; gq += 2) {
+        const float4 a0 = *reinterpret_cast<const float4*>(st + gq * 8), a1 = *reinterpret_cast<const float4*>(st + gq * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(st + gq * 8 + 8), b1 = *reinterpret_cast<const float4*>(st + gq * 8 + 12);
+        const float va[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float vb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        emit(va, gq);
+        emit(vb, gq + 1);
       }
+      const float vt[8] = {st[80], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // tap 80 + the 7 zero pads
+      emit(vt, 10);
     }
-    if (HALF != 2) named_bar_sync(1 + c.lg, 64);
   }
 }
 
@@ -380,8 +397,7 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
     }
   } else {
     // ------------------------------------------------------------------ epilogue: gather + bilinear blend + store
-    // thread = pixel = TMEM lane; with kSplitEpi two warps per lane group share the pixels: half 0 produces the taps
-    // i = 0..4, half 1 the taps i = 5..8
+    // thread = pixel = TMEM lane
     const int lg = warp & 3, ml = lg * 32 + lane;
     auto load_coord = [&](int tile, float& ox, float& oy, bool& v) {
       const int b = tile / tpi, tr = tile - b * tpi;
@@ -403,9 +419,7 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
       mbar_wait(&ti_full[slot], (n >> 1) & 1);
       if (!ti[slot].overflow) {
         EpiCtx c{p, &ti[slot], scratch, stage, acc_full, acc_empty, tmem_base, b, y0, x0, lg, ml, lane, valid, cx, cy};
-        if (!kSplitEpi) lookup_epilogue<2>(c, ch);
-        else if (warp - 2 < 4) lookup_epilogue<0>(c, ch);
-        else lookup_epilogue<1>(c, ch);
+        lookup_epilogue(c, ch);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&ti_empty[slot]);
