@@ -58,7 +58,10 @@ corr_lookup_tile_kernel(const float* __restrict__ f1_cl, const float* __restrict
   const int p = tid >> 2, s = tid & 3;
   const int b = blockIdx.z;
   // fallback mode: only the 8x16 tiles flagged by the tensor-core kernel are recomputed here
-  if (flags != nullptr && flags[(b * fty + blockIdx.y) * ftx + (blockIdx.x >> 1)] == 0) return;
+  if (flags != nullptr) {                // per 8x16 tile: one flag per pyramid level, any set -> recompute the tile
+    const int4 f = reinterpret_cast<const int4*>(flags)[(b * fty + blockIdx.y) * ftx + (blockIdx.x >> 1)];
+    if ((f.x | f.y | f.z | f.w) == 0) return;
+  }
   const int py = blockIdx.y * kTile + (p >> 3), px = blockIdx.x * kTile + (p & 7);
   const bool valid = py < H && px < W;
   const int P = H * W;

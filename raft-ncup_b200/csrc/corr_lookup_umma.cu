@@ -4,18 +4,27 @@
 // positions that covers every pixel's 10x10 lattice window, then each pixel gathers its own window from the
 // accumulator and blends it bilinearly.
 //
-//   A  = fmap1 tile      [128 px][256 ch] halves, TMA box {64,16,8,1} x 4 K-blocks, resident for the whole tile
-//   B  = fmap2^l box     chunks of 256 positions x 256 ch, TMA boxes {64, BW, CR, 1}; out-of-image positions are
-//                        zero-filled by TMA = the reference's zero padding (grid_sample padding_mode='zeros')
-//   D  = [128][256] fp32 in TMEM, double buffered: the MMA warp fills one chunk while the epilogue drains the other
+//   A  = fmap1 tile      [128 px][256 ch] halves, TMA box {64,16,8,1} x 4 K-blocks, resident while its levels are processed
+//   B  = fmap2^l box     chunks of <= 256 positions x 256 ch streamed through a ring of 32 KB stages as 2-row TMA boxes
+//                        {64, BW, 2, 1}; only the box rows some window needs are loaded and multiplied (N is set per chunk);
+//                        out-of-image positions are zero-filled by TMA = the reference's zero padding (grid_sample
+//                        padding_mode='zeros')
+//   D  = [128][<=256] fp32 in TMEM, double buffered: the MMA warp fills one chunk while the epilogue drains the other
 //
-// Epilogue (thread = pixel = TMEM lane): one box row (BW columns) at a time is read with tcgen05.ld, parked in a
-// thread-private column of shared memory (dynamic addressing), the 10 lattice values of the pixel's window row are read
-// back, interpolated in x, combined with the previous row in y -> 9 outputs (fixed j, i = 0..8) into a staging row,
-// which is written out per level as 16-byte groups of hi/lo split halves (the tcgen05 convolutions' operand format).
+// Persistent CTAs (one per SM) walk work units (tile, level); producer / MMA / epilogue warps are decoupled by mbarrier
+// rings, so the loads and MMAs of the next unit overlap the epilogue of the current one (see the kernel's comment).
+//
+// Epilogue (thread = pixel = TMEM lane): two box rows (BW columns each) at a time are read with tcgen05.ld and parked in
+// a thread-private shared-memory row (128-bit stores; dynamic addressing is what shared memory is needed for), the 10
+// lattice values of the pixel's window row are read back, interpolated in x, combined with the previous row in y -> 9
+// outputs (fixed j, i = 0..8) into a staging row, which is written out per level as 16-byte groups of hi/lo split
+// halves (the tcgen05 convolutions' operand format).
 //
 // Tiles whose windows do not fit the fixed boxes (incoherent flow) are flagged and recomputed by the exact CUDA-core
 // kernel (corr_lookup.cu), so the result never depends on the coherence assumption.
+//
+// Measured on B200 (B=8, 55x128, profiles/): the three engines are balanced within 2x of each other — L2->SM operand
+// traffic ~45 us, tensor pipe ~45 us, epilogue ~70 us per launch when each runs alone, ~95 us together.
 //
 // Precision: fmaps are rounded once to fp16 (fp32 accumulate): 2.4e-4 EPE after 32 iterations in SURVEY.md Appendix D.
 #include <type_traits>
@@ -29,7 +38,11 @@ using namespace rnc::umma;
 
 // One epilogue warp per TMEM lane group.  (A second warp per lane group splitting the slow window index i was measured
 // on B200 at 0.105 ms vs 0.106 ms per launch: it duplicates the accumulator-row parking, which is most of the work.)
+#ifdef RNC_PROBE_DUPEPI
+constexpr int kEpiWarps = 8;   // probe: a second epilogue warp per lane group repeats the work on aliased buffers
+#else
 constexpr int kEpiWarps = 4;
+#endif
 constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA + TMEM, then the epilogue warps
 constexpr int kTY = 8, kTX = 16;         // query tile (level-0 pixels)
 constexpr int kD = 256;                  // feature channels
@@ -44,32 +57,50 @@ __host__ __device__ constexpr int chunk_rows(int l) { return l == 0 ? 8 : l == 1
 __host__ __device__ constexpr int n_chunks(int l) { return l == 0 ? 3 : l == 1 ? 2 : 1; }
 __host__ __device__ constexpr int box_h(int l) { return chunk_rows(l) * n_chunks(l); }
 __host__ __device__ constexpr int chunk_n(int l) { return box_w(l) * chunk_rows(l); }
-constexpr int kStages = 2;               // B ring (a third stage does not fit beside the two-row scratch and measures the same)
+#ifndef RNC_LOOKUP_TMAROWS
+#define RNC_LOOKUP_TMAROWS 2
+#endif
+#ifndef RNC_LOOKUP_STAGES
+#define RNC_LOOKUP_STAGES 2
+#endif
+constexpr int kStages = RNC_LOOKUP_STAGES;   // B ring (a third stage does not fit beside the two-row scratch and measures the same)
 constexpr int kATile = 128 * 64 * 2;     // 16 KB per K block
 constexpr int kBStage = 256 * 64 * 2;    // 32 KB: 256 positions x 64 halves
 constexpr int kLvlStride = 88;           // channels per level in the output row (81 taps + 7 zero pads): 16-byte groups
+#ifndef RNC_LOOKUP_TIRING
+#define RNC_LOOKUP_TIRING 4
+#endif
+constexpr int kTiRing = RNC_LOOKUP_TIRING;    // unit records in flight between the producer and its consumers (power of two)
+constexpr int kTiShift = kTiRing == 2 ? 1 : kTiRing == 4 ? 2 : 3;
 constexpr int kSmemA = kKB * kATile;                         // 64 KB
 constexpr int kSmemB = kStages * kBStage;                    // 96 KB
 // Epilogue buffers are pixel-major with 16-byte aligned rows, so a thread moves its data with 128-bit accesses:
 //   scratch [pixel][68]: two box rows (32 words each) of the accumulator; 68 = 4*17 -> the 8 lanes of a quarter warp hit
 //                        8 distinct bank quads
 //   stage   [pixel][84]: the level's 81 taps (+3);       84 = 4*21 -> same property
-constexpr int kScrStride = 68, kStgStride = 84;
+#ifndef RNC_LOOKUP_STGSTRIDE
+#define RNC_LOOKUP_STGSTRIDE 84
+#endif
+constexpr int kScrStride = 68, kStgStride = RNC_LOOKUP_STGSTRIDE;
 constexpr int kSmemScratch = 128 * kScrStride * 4;           // 34 KB
 constexpr int kSmemStage = 128 * kStgStride * 4;             // 42 KB
+#ifdef RNC_PROBE_NOEPI
+constexpr int kSmemTotal = kSmemA + kSmemB + 1024 + 512;     // probe: the epilogue buffers are never touched
+#else
 constexpr int kSmemTotal = kSmemA + kSmemB + kSmemScratch + kSmemStage + 1024 + 512;
+#endif
 
 struct Params {
   const float* coords;                 // [B][2][H][W]
   __half* out_hi; __half* out_lo; int ldo;
-  int* flags;                          // [tiles]: 1 = recompute this tile with the exact kernel
+  int* flags;                          // [tiles][4 levels]: 1 = recompute this tile with the exact kernel
   int B, H, W, tiles_x, tiles_y;
+  int tile_major;                      // unit order: 1 = the four levels of a tile back to back on one CTA (A loaded once per tile)
   float scale;
 };
 
-struct TileInfo {                      // shared: per-level origin of the tile's union box (0,0 when no window is live)
-  int bx0[kLevels], by0[kLevels];
-  int overflow, pad[7];
+struct TileInfo {                      // shared: origin of the unit's union box (0,0 when no window is live), the box rows
+  int bx0, by0, overflow, nrows;       // actually needed (even, <= box_h; 0 = no live window): only those are loaded / multiplied
 };
 
 // Window origin of one pixel at one level (shared by the producer's box computation and the epilogue's gather).
@@ -142,13 +173,18 @@ __device__ __forceinline__ void lookup_level_rows(const EpiCtx& c, int& ch, int 
       *reinterpret_cast<uint4*>(sc + half * 32 + 4 * g4) = make_uint4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
   };
 
-  for (int cc = 0; cc < n_chunks(l); ++cc, ++ch) {
+  const int nch = (c.ti->nrows + cr - 1) / cr;
+  for (int cc = 0; cc < nch; ++cc, ++ch) {
     const int buf = ch & 1, use = ch >> 1;
     mbar_wait(&c.acc_full[buf], use & 1);
     tcgen05_fence_after();
     const int r0 = max(0, row_lo - cc * cr), r1 = min(cr - 1, row_hi - cc * cr);   // rows of this chunk the warp needs
     const uint32_t tbase = c.tmem_base + (static_cast<uint32_t>(c.lg * 32) << 16) + buf * 256;
+#ifdef RNC_PROBE_NOEPI
+    if (false) {
+#else
     if (r0 <= r1) {
+#endif
       // software pipeline: the TMEM loads of the next two rows are in flight while this pair is processed
       uint32_t va[32] = {}, vb[32] = {};
       tmem_row_issue<BW>(tbase + r0 * BW, va);
@@ -172,59 +208,80 @@ __device__ __forceinline__ void lookup_level_rows(const EpiCtx& c, int& ch, int 
   }
 }
 
-// Epilogue of one warp (thread = pixel = TMEM lane) for one tile: all levels, rows then write-out.
-__device__ __forceinline__ void lookup_epilogue(const EpiCtx& c, int& ch) {
+// Epilogue of one warp (thread = pixel = TMEM lane) for one unit = (tile, level l): rows, then write-out.
+__device__ __forceinline__ void lookup_epilogue(const EpiCtx& c, int& ch, int l) {
   const Params& p = c.p;
   const int HW = p.H * p.W;
   float* st = c.stage + c.ml * kStgStride;
   const int qy = c.y0 + (c.ml >> 4), qx = c.x0 + (c.ml & 15);
-  float inv = 1.f;
-#pragma unroll 1
-  for (int l = 0; l < kLevels; ++l) {
-    const int Hl = p.H >> l, Wl = p.W >> l;
-    const float sx = c.cx * inv, sy = c.cy * inv;
-    const float ax = sx - floorf(sx), ay = sy - floorf(sy);
-    int ix0, iy0;
-    const bool empty = !window_origin(c.cx, c.cy, inv, Hl, Wl, ix0, iy0);
-    inv *= 0.5f;
-    const int ox = ix0 - c.ti->bx0[l], oy = iy0 - c.ti->by0[l];
-    const bool live = c.valid && !empty;
-    if (c.valid && empty) {
-      for (int k = 0; k < kS * kS; ++k) st[k] = 0.f;
-    }
-    if (l == 0) lookup_level_rows<box_w(0)>(c, ch, l, live, ox, oy, ax, ay);
-    else if (l == 1) lookup_level_rows<box_w(1)>(c, ch, l, live, ox, oy, ax, ay);
-    else lookup_level_rows<box_w(2)>(c, ch, l, live, ox, oy, ax, ay);
-    static_assert(box_w(2) == box_w(3), "levels 2 and 3 share the row code");
-    // ---- level done.  The level occupies kLvlStride (= 88, a multiple of 8) channels of the output row: 81 taps + 7 zero
-    // pads, so every group of 8 channels is one aligned 16-byte store per plane.  Two groups per step (independent chains).
-    if (qy < p.H && qx < p.W) {
-      const size_t base = (static_cast<size_t>(c.b) * HW + qy * p.W + qx) * p.ldo + l * kLvlStride;
-      auto emit = [&](const float (&v)[8], int gq) {
-        __half2 hh[4], ll[4];
+  const float inv = 1.f / static_cast<float>(1 << l);
+  const float sx = c.cx * inv, sy = c.cy * inv;
+  const float ax = sx - floorf(sx), ay = sy - floorf(sy);
+  int ix0, iy0;
+  const bool empty = !window_origin(c.cx, c.cy, inv, p.H >> l, p.W >> l, ix0, iy0);
+  const int ox = ix0 - c.ti->bx0, oy = iy0 - c.ti->by0;
+  const bool live = c.valid && !empty;
+  if (c.valid && empty) {
+    for (int k = 0; k < kS * kS; ++k) st[k] = 0.f;
+  }
+  if (l == 0) lookup_level_rows<box_w(0)>(c, ch, l, live, ox, oy, ax, ay);
+  else if (l == 1) lookup_level_rows<box_w(1)>(c, ch, l, live, ox, oy, ax, ay);
+  else lookup_level_rows<box_w(2)>(c, ch, l, live, ox, oy, ax, ay);
+  static_assert(box_w(2) == box_w(3), "levels 2 and 3 share the row code");
+  // ---- The level occupies kLvlStride (= 88, a multiple of 8) channels of the output row: 81 taps + 7 zero pads, so every
+  // group of 8 channels is one aligned 16-byte store per plane.  Two groups per step (independent chains).
+#ifdef RNC_PROBE_NOEPI
+  if (false) {
+#else
+  if (qy < p.H && qx < p.W) {
+#endif
+    const size_t base = (static_cast<size_t>(c.b) * HW + qy * p.W + qx) * p.ldo + l * kLvlStride;
+    auto emit = [&](const float (&v)[8], int gq) {
+      __half2 hh[4], ll[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float v0 = fminf(fmaxf(v[2 * j], -65504.f), 65504.f), v1 = fminf(fmaxf(v[2 * j + 1], -65504.f), 65504.f);
-          hh[j] = __floats2half2_rn(v0, v1);
-          const float2 back = __half22float2(hh[j]);
-          ll[j] = __floats2half2_rn(v0 - back.x, v1 - back.y);
-        }
-        *reinterpret_cast<uint4*>(p.out_hi + base + gq * 8) = *reinterpret_cast<uint4*>(hh);
-        *reinterpret_cast<uint4*>(p.out_lo + base + gq * 8) = *reinterpret_cast<uint4*>(ll);
-      };
+      for (int j = 0; j < 4; ++j) {
+        const float v0 = fminf(fmaxf(v[2 * j], -65504.f), 65504.f), v1 = fminf(fmaxf(v[2 * j + 1], -65504.f), 65504.f);
+        hh[j] = __floats2half2_rn(v0, v1);
+        const float2 back = __half22float2(hh[j]);
+        ll[j] = __floats2half2_rn(v0 - back.x, v1 - back.y);
+      }
+      *reinterpret_cast<uint4*>(p.out_hi + base + gq * 8) = *reinterpret_cast<uint4*>(hh);
+      *reinterpret_cast<uint4*>(p.out_lo + base + gq * 8) = *reinterpret_cast<uint4*>(ll);
+    };
 #pragma unroll 1
-      for (int gq = 0; gq < 10; gq += 2) {
+    for (int gq = 0; gq < 10; gq += 2) {
+      float va[8], vb[8];
+      if (kStgStride % 4 == 0) {
         const float4 a0 = *reinterpret_cast<const float4*>(st + gq * 8), a1 = *reinterpret_cast<const float4*>(st + gq * 8 + 4);
         const float4 b0 = *reinterpret_cast<const float4*>(st + gq * 8 + 8), b1 = *reinterpret_cast<const float4*>(st + gq * 8 + 12);
-        const float va[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float vb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        emit(va, gq);
-        emit(vb, gq + 1);
+        va[0] = a0.x; va[1] = a0.y; va[2] = a0.z; va[3] = a0.w; va[4] = a1.x; va[5] = a1.y; va[6] = a1.z; va[7] = a1.w;
+        vb[0] = b0.x; vb[1] = b0.y; vb[2] = b0.z; vb[3] = b0.w; vb[4] = b1.x; vb[5] = b1.y; vb[6] = b1.z; vb[7] = b1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { va[j] = st[gq * 8 + j]; vb[j] = st[gq * 8 + 8 + j]; }
       }
-      const float vt[8] = {st[80], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // tap 80 + the 7 zero pads
-      emit(vt, 10);
+      emit(va, gq);
+      emit(vb, gq + 1);
     }
+    const float vt[8] = {st[80], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // tap 80 + the 7 zero pads
+    emit(vt, 10);
   }
+}
+
+// Work units.  A unit is (tile, level): 3, 2, 1, 1 accumulator chunks.  Units are listed level-major (all level-0 units
+// first = longest first) and dealt to the CTAs in snake order (round k runs left-to-right for even k, right-to-left for
+// odd k): a single image (56 tiles of 7 chunks) still fills all 148 SMs, the busiest CTA getting 3 chunks, and for B=8
+// the busiest CTA gets 23 chunks where whole tiles would give it 28.  The alternative tile-major order (the four levels
+// of a tile back to back on one CTA, A loaded once per tile) is selectable from the host.
+// Returns the k-th unit of this CTA or -1 (none in round k).
+__device__ __forceinline__ int unit_at(int k, int nunits, int tile_major) {
+  const int G = gridDim.x, c = blockIdx.x;
+  if (tile_major) {
+    const int ntiles = nunits / kLevels, tile = (k / kLevels) * G + c;
+    return tile < ntiles ? (k % kLevels) * ntiles + tile : -1;
+  }
+  const int g = k * G + ((k & 1) ? G - 1 - c : c);
+  return g < nunits ? g : -1;
 }
 
 // Persistent kernel: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The three roles run decoupled
@@ -243,17 +300,17 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
   unsigned char* sB = smem + kSmemA;
   float* scratch = reinterpret_cast<float*>(smem + kSmemA + kSmemB);
   float* stage = reinterpret_cast<float*>(smem + kSmemA + kSmemB + kSmemScratch);
-  unsigned char* tail = smem + kSmemA + kSmemB + kSmemScratch + kSmemStage;
+  unsigned char* tail = smem + kSmemTotal - 1024 - 512;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);       // [kKB]
   uint64_t* a_empty = a_full + kKB;                           // [kKB]
   uint64_t* b_full = a_empty + kKB;
   uint64_t* b_empty = b_full + kStages;
   uint64_t* acc_full = b_empty + kStages;
   uint64_t* acc_empty = acc_full + 2;
-  uint64_t* ti_full = acc_empty + 2;                          // [2]
-  uint64_t* ti_empty = ti_full + 2;                           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ti_empty + 2);
-  TileInfo* ti = reinterpret_cast<TileInfo*>(tmem_slot + 2);  // [2]
+  uint64_t* ti_full = acc_empty + 2;                          // [kTiRing]
+  uint64_t* ti_empty = ti_full + kTiRing;                     // [kTiRing]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ti_empty + kTiRing);
+  TileInfo* ti = reinterpret_cast<TileInfo*>(tmem_slot + 2);  // [kTiRing]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tpi = p.tiles_x * p.tiles_y;
@@ -263,10 +320,8 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
   if (threadIdx.x == 0) {
     for (int kb = 0; kb < kKB; ++kb) { mbar_init(&a_full[kb], 1); mbar_init(&a_empty[kb], 1); }
     for (int s = 0; s < kStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps);
-      mbar_init(&ti_full[i], 1); mbar_init(&ti_empty[i], kEpiWarps + 1);
-    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
+    for (int i = 0; i < kTiRing; ++i) { mbar_init(&ti_full[i], 1); mbar_init(&ti_empty[i], kEpiWarps + 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -274,6 +329,10 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  const int nunits = ntiles * kLevels;
+  const int tm = p.tile_major;
+  const int rounds = tm ? ((ntiles + gridDim.x - 1) / gridDim.x) * kLevels : (nunits + gridDim.x - 1) / gridDim.x;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer (warp-uniform loops, one elected lane issues)
@@ -290,110 +349,184 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
         oy[j] = v ? clamp_coord(__ldg(p.coords + (static_cast<size_t>(b) * 2 + 1) * HW + py * p.W + px)) : 0.f;
       }
     };
-    if (static_cast<int>(blockIdx.x) < ntiles) load_coords(blockIdx.x, pcx, pcy);
-    int it = 0, n = 0, nv = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
-      const int b = tile / tpi, tr = tile - b * tpi;
-      const int y0 = (tr / p.tiles_x) * kTY, x0 = (tr % p.tiles_x) * kTX;
-      int bx0[kLevels], by0[kLevels];
-      int ov = 0;
-      {
-        float inv = 1.f;
+    // record of one unit: union box origin, rows needed, overflow
+    struct Rec { int bx0, by0, nrows, ov; };
+    auto make_rec = [&](int unit, const float (&ux)[4], const float (&uy)[4]) {
+      const int l = unit / ntiles;
+      const float inv = 1.f / static_cast<float>(1 << l);
+      int lx0 = 0x7fffffff, ly0 = 0x7fffffff, lx1 = -0x7fffffff, ly1 = -0x7fffffff;
 #pragma unroll
-        for (int l = 0; l < kLevels; ++l) {
-          int lx0 = 0x7fffffff, ly0 = 0x7fffffff, lx1 = -0x7fffffff, ly1 = -0x7fffffff;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            int ix0, iy0;
-            if (pcx[j] == pcx[j] && window_origin(pcx[j], pcy[j], inv, p.H >> l, p.W >> l, ix0, iy0)) {   // NaN marks a pixel outside the image
-              lx0 = min(lx0, ix0); ly0 = min(ly0, iy0); lx1 = max(lx1, ix0 + kG - 1); ly1 = max(ly1, iy0 + kG - 1);
-            }
-          }
-          inv *= 0.5f;
-          lx0 = __reduce_min_sync(0xffffffffu, lx0); ly0 = __reduce_min_sync(0xffffffffu, ly0);
-          lx1 = __reduce_max_sync(0xffffffffu, lx1); ly1 = __reduce_max_sync(0xffffffffu, ly1);
-          const bool any = lx1 >= lx0;
-          if (any && (lx1 - lx0 + 1 > box_w(l) || ly1 - ly0 + 1 > box_h(l))) ov = 1;
-          bx0[l] = any ? lx0 : 0; by0[l] = any ? ly0 : 0;
+      for (int j = 0; j < 4; ++j) {
+        int ix0, iy0;
+        if (ux[j] == ux[j] && window_origin(ux[j], uy[j], inv, p.H >> l, p.W >> l, ix0, iy0)) {   // NaN marks a pixel outside the image
+          lx0 = min(lx0, ix0); ly0 = min(ly0, iy0); lx1 = max(lx1, ix0 + kG - 1); ly1 = max(ly1, iy0 + kG - 1);
         }
       }
-      // the next tile's coords travel while this tile's loads are issued
-      if (tile + static_cast<int>(gridDim.x) < ntiles) load_coords(tile + gridDim.x, pcx, pcy);
-      const int slot = n & 1;
-      mbar_wait(&ti_empty[slot], ((n >> 1) & 1) ^ 1);
+      lx0 = __reduce_min_sync(0xffffffffu, lx0); ly0 = __reduce_min_sync(0xffffffffu, ly0);
+      lx1 = __reduce_max_sync(0xffffffffu, lx1); ly1 = __reduce_max_sync(0xffffffffu, ly1);
+      const bool any = lx1 >= lx0;
+      Rec r;
+      r.ov = any && (lx1 - lx0 + 1 > box_w(l) || ly1 - ly0 + 1 > box_h(l)) ? 1 : 0;
+      r.bx0 = any ? lx0 : 0; r.by0 = any ? ly0 : 0;
+#ifdef RNC_PROBE_NOTRIM
+      r.nrows = any ? box_h(l) : 0;
+#else
+      r.nrows = any ? min((ly1 - ly0 + 2) & ~1, box_h(l)) : 0;
+#endif
+      return r;
+    };
+    int n = 0;
+    auto publish = [&](int unit, const Rec& r) {
+      const int slot = n & (kTiRing - 1);
+      mbar_wait(&ti_empty[slot], ((n >> kTiShift) & 1) ^ 1);
       if (lane == 0) {
-#pragma unroll
-        for (int l = 0; l < kLevels; ++l) { ti[slot].bx0[l] = bx0[l]; ti[slot].by0[l] = by0[l]; }
-        ti[slot].overflow = ov;
-        p.flags[tile] = ov;
-        mbar_arrive(&ti_full[slot]);         // release: the tile record is visible to the waiters
+        ti[slot].bx0 = r.bx0; ti[slot].by0 = r.by0; ti[slot].overflow = r.ov; ti[slot].nrows = r.nrows;
+        const int l = unit / ntiles;
+        p.flags[(unit - l * ntiles) * kLevels + l] = r.ov;
+        mbar_arrive(&ti_full[slot]);         // release: the unit record is visible to the waiters
       }
       __syncwarp();
-      if (ov) continue;                      // the exact kernel recomputes this tile
+      ++n;
+    };
+    // The record of unit k+1 is computed and published while unit k's loads are in flight (after its first kStages B
+    // loads, when the ring is full and this warp would only wait), from coords fetched one unit earlier: nothing but
+    // barrier waits sits between the last load of a unit and the first load of the next.
+    int unit = unit_at(0, nunits, tm), next = -1;
+    Rec cur = {0, 0, 0, 0}, nxt = {0, 0, 0, 0};
+    if (unit >= 0) {
+      load_coords(unit % ntiles, pcx, pcy);
+      cur = make_rec(unit, pcx, pcy);
+      publish(unit, cur);
+      next = unit_at(1, nunits, tm);
+      if (next >= 0) load_coords(next % ntiles, pcx, pcy);
+    }
+    int it = 0, na = 0;
+    for (int k = 0; unit >= 0; ++k) {
+      const int l = unit / ntiles, tile = unit - l * ntiles;
+      const int b = tile / tpi, tr = tile - b * tpi;
+      const int y0 = (tr / p.tiles_x) * kTY, x0 = (tr % p.tiles_x) * kTX;
+      const int bx0 = cur.bx0, by0 = cur.by0, nrows = cur.nrows;
+      const bool skip = cur.ov || nrows == 0;    // overflow: the exact kernel recomputes this tile; no rows: all-zero level
+      const bool load_a = tm ? l == 0 : !skip;
+      if (load_a) {
 #pragma unroll
-      for (int kb = 0; kb < kKB; ++kb) {
-        mbar_wait(&a_empty[kb], (nv & 1) ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(&a_full[kb], kATile);
-          tma_load_4d(sA + kb * kATile, &mF1, &a_full[kb], kb * 64, x0, y0, b);
+        for (int kb = 0; kb < kKB; ++kb) {
+          mbar_wait(&a_empty[kb], (na & 1) ^ 1);
+          if (elect_one()) {
+#ifdef RNC_PROBE_NOLOAD
+            mbar_arrive(&a_full[kb]);
+#else
+            mbar_expect_tx(&a_full[kb], kATile);
+            tma_load_4d(sA + kb * kATile, &mF1, &a_full[kb], kb * 64, x0, y0, b);
+#endif
+          }
+          __syncwarp();
         }
-        __syncwarp();
+        ++na;
       }
-#pragma unroll
-      for (int l = 0; l < kLevels; ++l) {
+      bool ahead_done = false;
+      int after = -1;
+      auto ahead = [&]() {
+        if (ahead_done) return;
+        ahead_done = true;
+        if (next >= 0) {
+          nxt = make_rec(next, pcx, pcy);
+          publish(next, nxt);
+          after = unit_at(k + 2, nunits, tm);
+          if (after >= 0) load_coords(after % ntiles, pcx, pcy);
+        }
+      };
+      if (!skip) {
+        // B: only the box rows some window needs, as 2-row TMA boxes (2 * bw positions = a multiple of 1024 bytes of the
+        // SWIZZLE_128B stage, so the pieces tile the stage exactly as one big box would)
         const CUtensorMap* map = l == 0 ? &mL0 : l == 1 ? &mL1 : l == 2 ? &mL2 : &mL3;
-        for (int c = 0; c < n_chunks(l); ++c)
+        const int cr = chunk_rows(l), bw = box_w(l);
+        int issued = 0;
+        for (int c = 0; c * cr < nrows; ++c) {
+          const int rows = min(cr, nrows - c * cr);
           for (int kb = 0; kb < kKB; ++kb, ++it) {
             const int s = it % kStages, ph = (it / kStages) & 1;
             mbar_wait(&b_empty[s], ph ^ 1);
             if (elect_one()) {
-              mbar_expect_tx(&b_full[s], chunk_n(l) * 128);
-              tma_load_4d(sB + s * kBStage, map, &b_full[s], kb * 64, bx0[l], by0[l] + c * chunk_rows(l), b);
+#ifdef RNC_PROBE_NOLOAD
+              mbar_arrive(&b_full[s]);
+#else
+#if RNC_LOOKUP_TMAROWS == 2
+              mbar_expect_tx(&b_full[s], rows * bw * 128);
+              for (int r2 = 0; r2 < rows; r2 += 2)
+                tma_load_4d(sB + s * kBStage + r2 * bw * 128, map, &b_full[s], kb * 64, bx0, by0 + c * cr + r2, b);
+#else
+              mbar_expect_tx(&b_full[s], cr * bw * 128);
+              tma_load_4d(sB + s * kBStage, map, &b_full[s], kb * 64, bx0, by0 + c * cr, b);
+#endif
+#endif
             }
             __syncwarp();
+            if (++issued == kStages) ahead();
           }
+        }
       }
-      ++nv;
+      ahead();
+      unit = next; cur = nxt; next = after;
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform loops, one elected lane issues)
     const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-    int it = 0, ch = 0, n = 0, nv = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
-      const int slot = n & 1;
-      mbar_wait(&ti_full[slot], (n >> 1) & 1);
-      const int ov = ti[slot].overflow;
+    int it = 0, ch = 0, n = 0, na = 0;
+    for (int k = 0; k < rounds; ++k) {
+      const int unit = unit_at(k, nunits, tm);
+      if (unit < 0) continue;
+      const int l = unit / ntiles;
+      const int slot = n & (kTiRing - 1);
+      mbar_wait(&ti_full[slot], (n >> kTiShift) & 1);
+      const int ov = ti[slot].overflow, nrows = ti[slot].nrows;
       __syncwarp();
       if (lane == 0) mbar_arrive(&ti_empty[slot]);
-      if (ov) continue;
-#pragma unroll
-      for (int l = 0; l < kLevels; ++l) {
-        // instruction descriptor: D = F32, A = B = F16, K-major, N = positions of this level's chunk, M = 128
-        const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(chunk_n(l) >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
-        for (int c = 0; c < n_chunks(l); ++c, ++ch) {
-          const bool first = l == 0 && c == 0, final = l == kLevels - 1 && c == n_chunks(l) - 1;
-          const int buf = ch & 1, use = ch >> 1;
-          mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
-          tcgen05_fence_after();
-          for (int kb = 0; kb < kKB; ++kb, ++it) {
-            const int s = it % kStages, ph = (it / kStages) & 1;
-            if (first) mbar_wait(&a_full[kb], nv & 1);
-            mbar_wait(&b_full[s], ph);
-            tcgen05_fence_after();
-            const uint64_t ad = smem_desc_sw128(a_base + kb * kATile), bd = smem_desc_sw128(b_base + s * kBStage);
-            if (elect_one()) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) umma_f16(tmem_base + buf * 256, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
-              umma_commit(&b_empty[s]);
-              if (final) umma_commit(&a_empty[kb]);   // this K block of A is free for the next tile
-            }
-            __syncwarp();
+      ++n;
+      const bool skip = ov || nrows == 0;
+      const bool load_a = tm ? l == 0 : !skip, free_a = tm ? l == kLevels - 1 : !skip;
+      if (skip) {                            // tile-major order: the A tile's barriers still turn over once per tile
+        if (load_a) {
+          for (int kb = 0; kb < kKB; ++kb) mbar_wait(&a_full[kb], na & 1);
+          ++na;
+        }
+        if (free_a) {
+          if (elect_one()) {
+            for (int kb = 0; kb < kKB; ++kb) umma_commit(&a_empty[kb]);
           }
-          if (elect_one()) umma_commit(&acc_full[buf]);
           __syncwarp();
         }
+        continue;
       }
-      ++nv;
+      const int cr = chunk_rows(l), nc = (nrows + cr - 1) / cr;
+      for (int c = 0; c < nc; ++c, ++ch) {
+        const bool first = c == 0, final = c == nc - 1;
+        // instruction descriptor: D = F32, A = B = F16, K-major, N = positions of the rows this chunk holds, M = 128
+        const uint32_t nn = min(cr, nrows - c * cr) * box_w(l);
+        const uint32_t idesc = (1u << 4) | ((nn >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+        const int buf = ch & 1, use = ch >> 1;
+        mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
+        tcgen05_fence_after();
+        for (int kb = 0; kb < kKB; ++kb, ++it) {
+          const int s = it % kStages, ph = (it / kStages) & 1;
+          if (first && load_a) mbar_wait(&a_full[kb], na & 1);
+          mbar_wait(&b_full[s], ph);
+          tcgen05_fence_after();
+          const uint64_t ad = smem_desc_sw128(a_base + kb * kATile), bd = smem_desc_sw128(b_base + s * kBStage);
+          if (elect_one()) {
+#pragma unroll
+#ifndef RNC_PROBE_NOMMA
+            for (int kk = 0; kk < 4; ++kk) umma_f16(tmem_base + buf * 256, ad + 2 * kk, bd + 2 * kk, idesc, (kb | kk) != 0);
+#endif
+            umma_commit(&b_empty[s]);
+            if (final && free_a) umma_commit(&a_empty[kb]);   // this K block of A is free for the next tile
+          }
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit(&acc_full[buf]);
+        __syncwarp();
+      }
+      if (load_a) ++na;
     }
   } else {
     // ------------------------------------------------------------------ epilogue: gather + bilinear blend + store
@@ -408,21 +541,33 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
     };
     float cx = 0.f, cy = 0.f, ncx = 0.f, ncy = 0.f;
     bool valid = false, nvalid = false;
-    if (static_cast<int>(blockIdx.x) < ntiles) load_coord(blockIdx.x, ncx, ncy, nvalid);
+    int unit = unit_at(0, nunits, tm);
+    if (unit >= 0) load_coord(unit % ntiles, ncx, ncy, nvalid);
     int ch = 0, n = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+    for (int k = 0; k < rounds; ++k) {
+      const int cur = unit;
       cx = ncx; cy = ncy; valid = nvalid;
-      if (tile + static_cast<int>(gridDim.x) < ntiles) load_coord(tile + gridDim.x, ncx, ncy, nvalid);
+      unit = unit_at(k + 1, nunits, tm);
+      if (unit >= 0) load_coord(unit % ntiles, ncx, ncy, nvalid);
+      if (cur < 0) continue;
+      const int l = cur / ntiles, tile = cur - l * ntiles;
       const int b = tile / tpi, tr = tile - b * tpi;
       const int y0 = (tr / p.tiles_x) * kTY, x0 = (tr % p.tiles_x) * kTX;
-      const int slot = n & 1;
-      mbar_wait(&ti_full[slot], (n >> 1) & 1);
+      const int slot = n & (kTiRing - 1);
+      mbar_wait(&ti_full[slot], (n >> kTiShift) & 1);
       if (!ti[slot].overflow) {
+#ifdef RNC_PROBE_DUPEPI
+        float* scr = warp >= 6 ? reinterpret_cast<float*>(sA) : scratch;
+        float* stg = warp >= 6 ? reinterpret_cast<float*>(sA + kSmemScratch) : stage;
+        EpiCtx c{p, &ti[slot], scr, stg, acc_full, acc_empty, tmem_base, b, y0, x0, lg, ml, lane, valid, cx, cy};
+#else
         EpiCtx c{p, &ti[slot], scratch, stage, acc_full, acc_empty, tmem_base, b, y0, x0, lg, ml, lane, valid, cx, cy};
-        lookup_epilogue(c, ch);
+#endif
+        lookup_epilogue(c, ch, l);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&ti_empty[slot]);
+      ++n;
     }
   }
 
@@ -462,7 +607,7 @@ extern "C" int rnc_f32_to_f16(const float* src, void* dst, size_t n, void* strea
 
 extern "C" size_t rnc_corr_lookup_umma_workspace_bytes(int B, int H, int W) {
   using namespace lookup_umma;
-  return static_cast<size_t>(B) * ((H + kTY - 1) / kTY) * ((W + kTX - 1) / kTX) * sizeof(int);
+  return static_cast<size_t>(B) * ((H + kTY - 1) / kTY) * ((W + kTX - 1) / kTX) * kLevels * sizeof(int);
 }
 
 static int sm_count() {
@@ -491,7 +636,7 @@ extern "C" int rnc_corr_lookup_umma_fwd(const void* f1h_cl, const void* f2h_pyr,
   if (D != kD || levels != kLevels || radius != kR) return RNC_ERR_UNSUPPORTED;
   if ((H >> (levels - 1)) < 1 || (W >> (levels - 1)) < 1 || ldo < levels * kLvlStride || (ldo & 7) || lvl_stride != kLvlStride) return RNC_ERR_BAD_SHAPE;
   if (!f1h_cl || !f2h_pyr || !f1_cl || !f2_pyr || !coords || !out_hi || !out_lo || !workspace) return RNC_ERR_BAD_POINTER;
-  if (!aligned16(f1h_cl) || !aligned16(f2h_pyr)) return RNC_ERR_BAD_POINTER;
+  if (!aligned16(f1h_cl) || !aligned16(f2h_pyr) || !aligned16(workspace)) return RNC_ERR_BAD_POINTER;
   if (workspace_bytes < rnc_corr_lookup_umma_workspace_bytes(B, H, W)) return RNC_ERR_WORKSPACE;
   if (!encode_fn()) return RNC_ERR_UNSUPPORTED;
 
@@ -502,13 +647,19 @@ extern "C" int rnc_corr_lookup_umma_fwd(const void* f1h_cl, const void* f2h_pyr,
   p.B = B; p.H = H; p.W = W;
   p.tiles_x = (W + kTX - 1) / kTX; p.tiles_y = (H + kTY - 1) / kTY;
   p.scale = 1.0f / sqrtf(static_cast<float>(D));
+  {
+    // Level-major snake order by default.  Tile-major (A loaded once per tile) measures the same inside the update loop
+    // and 10% slower alone (B=8, 55x128: 0.109 vs 0.097 ms); kept as a developer override, RNC_LOOKUP_SCHED=tile.
+    static const char* env = getenv("RNC_LOOKUP_SCHED");
+    p.tile_major = env != nullptr && env[0] == 't';
+  }
 
   CUtensorMap maps[5];
   bool ok = make_act_map(&maps[0], f1h_cl, kD, kD, B, H, W, kTX, kTY);
   size_t off = 0;
   for (int l = 0; l < kLevels; ++l) {
     const int Hl = H >> l, Wl = W >> l;
-    ok = ok && make_act_map(&maps[1 + l], static_cast<const __half*>(f2h_pyr) + off, kD, kD, B, Hl, Wl, box_w(l), chunk_rows(l));
+    ok = ok && make_act_map(&maps[1 + l], static_cast<const __half*>(f2h_pyr) + off, kD, kD, B, Hl, Wl, box_w(l), RNC_LOOKUP_TMAROWS == 2 ? 2 : chunk_rows(l));
     off += static_cast<size_t>(B) * Hl * Wl * kD;
   }
   if (!ok) return RNC_ERR_BAD_SHAPE;
@@ -516,7 +667,7 @@ extern "C" int rnc_corr_lookup_umma_fwd(const void* f1h_cl, const void* f2h_pyr,
   static unsigned long long done = 0;
   if (int st = ensure_dyn_smem(corr_lookup_umma_kernel, kSmemTotal, &done)) return st;
   const int ntiles = B * p.tiles_x * p.tiles_y;
-  const int grid = ntiles < sm_count() ? ntiles : sm_count();   // persistent: one CTA per SM
+  const int grid = ntiles * kLevels < sm_count() ? ntiles * kLevels : sm_count();   // persistent: one CTA per SM
   corr_lookup_umma_kernel<<<grid, kThreads, kSmemTotal, as_stream(stream)>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
   if (int st = after_launch()) return st;
   // exact recomputation of the tiles the fixed boxes could not cover

@@ -143,6 +143,27 @@ def test_sintel_shape_32_iters_both_engines(mode, monkeypatch):
     assert e < 1e-3
 
 
+def test_kitti_shape_24_iters_warm_start():
+    """KITTI frames (375x1242 -> 376x1248 with the 'kitti' padder, evaluate.py:125; 47x156 at 1/8: ragged in both tile
+    directions), 24 iterations as evaluate.py:117 runs them, with a non-zero flow_init, vs the CPU oracle."""
+    from utils.utils import InputPadder
+    m = build_model("raft_nc_dbl").to(DEV)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    im1, im2 = frames(1, 375, 1242)
+    padder = InputPadder(im1.shape, "kitti")
+    p1, p2 = padder.pad(im1, im2)
+    assert p1.shape[-2:] == (376, 1248)
+    g = torch.Generator().manual_seed(5)
+    init = torch.randn(1, 2, 47, 156, generator=g) * 1.5
+    with torch.no_grad():
+        lo, up = m(p1.to(DEV), p2.to(DEV), iters=24, flow_init=init.to(DEV), test_mode=True)
+    olo, oup, _ = orc.raft_forward(sd, p1, p2, iters=24, model="raft_nc_dbl", flow_init=init, upsample_every_iter=False)
+    e = epe(up.cpu(), oup)
+    print(f"kitti shape: EPE flow_up vs oracle {e:.3e} (|flow_up| {oup.abs().mean():.2f})")
+    assert e < 1e-3 and epe(lo.cpu(), olo) < 2e-4
+    assert padder.unpad(up).shape[-2:] == (375, 1242)
+
+
 # ----------------------------------------------------------------------------- tensor-core correlation lookup
 
 
