@@ -33,6 +33,7 @@ struct Params {
   int nblk0, nblk;                    // 64-channel blocks in segment 0 / total
   int a_plane, SA, SB;                // bytes per A half-plane stage (rows*128, 1024-aligned), ring depths
   int use_base_offset;
+  int probe_nob;                      // developer probe (RNC_CONV_PROBE_NOB=1): skip the weight loads after the first ring fill
   int cout, epilogue;
   float unscale;
   const float* bias;
@@ -145,9 +146,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
               mbar_wait(&b_empty[sb], pb ^ 1);
               const int kcol = (tap * p.nblk + cb) * kBK;
               if (elect_one()) {
-                mbar_expect_tx(&b_full[sb], 2 * C::kBTile);
-                tma_load_2d(sB + sb * 2 * C::kBTile, &mBh, &b_full[sb], kcol, n0);
-                tma_load_2d(sB + sb * 2 * C::kBTile + C::kBTile, &mBl, &b_full[sb], kcol, n0);
+                if (p.probe_nob && b_it > p.SB) {
+                  mbar_arrive(&b_full[sb]);
+                } else {
+                  mbar_expect_tx(&b_full[sb], 2 * C::kBTile);
+                  tma_load_2d(sB + sb * 2 * C::kBTile, &mBh, &b_full[sb], kcol, n0);
+                  tma_load_2d(sB + sb * 2 * C::kBTile + C::kBTile, &mBl, &b_full[sb], kcol, n0);
+                }
               }
               __syncwarp();
             }
@@ -417,6 +422,40 @@ static int launch(const CUtensorMap* maps, Params& p, cudaStream_t stream, int m
 
 using namespace rnc;
 
+// Column-tile width.  The widest tile that divides coutpad is the default; a narrower one (more, smaller work items per
+// pixel tile) wins when the grid is under-filled (small batches: 56 pixel tiles on 148 SMs), when the tile count just
+// misses a multiple of the SM count (448 tiles = 4 rounds of 256 columns but 7 half-size rounds), or when K is so short
+// that the single-buffered 256-column epilogue dominates (1x1 layers).  Cost model in K-step units, fitted to B200
+// measurements (tools/bn_probe.py): per K-step 1.0 / 0.77 / 0.53 / 0.36 / 0.30 for 256 / 192 / 128 / 64 / 32 columns, + 3
+// K-steps of exposed epilogue for tiles wider than 128 columns (one TMEM accumulator pair), + 0.5 per item, x1.08 when the
+// A tile is loaded more than once.
+static int choose_bn(const rnc_conv_umma_desc& d, int bn_max, int stride) {
+  if (d.flags & RNC_CONV_SPLIT_N) return bn_max == 256 ? 128 : bn_max;
+  const int taps = d.kh * d.kw, ksteps = taps * ((d.c0 + 63) / 64 + (d.c1 + 63) / 64);
+  int TW, TH;
+  if (stride == 1 && (d.flags & RNC_CONV_NO_HALO) == 0 && d.kw > 1 && d.W > 64) { TW = 128; TH = 1; }
+  else if (stride == 1 && (d.flags & RNC_CONV_NO_HALO) == 0 && d.kw == 1 && d.kh > 1 && d.W >= 16 && d.H >= 8) { TW = 16; TH = 8; }
+  else { TW = 8; while (TW < d.W && TW < umma::kBM) TW <<= 1; TH = umma::kBM / TW; }
+  const long ntiles = static_cast<long>(d.B) * ((d.W + TW - 1) / TW) * ((d.H + TH - 1) / TH);
+  const int sms = umma::sm_count();
+  static const int cand[5] = {256, 192, 128, 64, 32};
+  static const float per_k[5] = {1.0f, 0.77f, 0.53f, 0.36f, 0.30f};
+  int best = bn_max;
+  float best_cost = 1e30f;
+  for (int i = 0; i < 5; ++i) {
+    const int bn = cand[i];
+    if (bn > bn_max || d.coutpad % bn != 0) continue;
+    if ((d.epilogue == RNC_EPI_TANH_RELU || d.epilogue == RNC_EPI_GRU_ZR) && bn < 64) continue;
+    const int ntn = d.coutpad / bn;
+    const long rounds = (ntiles * ntn + sms - 1) / sms;
+    float item = ksteps * per_k[i] + 0.5f + (bn > 128 ? 3.0f * bn / 256.0f : 0.f);
+    if (ntn > 1) item *= 1.08f;
+    const float cost = rounds * item;
+    if (cost < best_cost * 0.97f) { best_cost = cost; best = bn; }     // wider wins near-ties
+  }
+  return best;
+}
+
 extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream) {
   using namespace rnc::umma;
   if (!desc) return RNC_ERR_BAD_POINTER;
@@ -435,6 +474,8 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   int bn;
   if (d.coutpad <= 32) bn = 32; else if (d.coutpad <= 64) bn = 64; else if (d.coutpad <= 128) bn = 128;
   else if (d.coutpad % 192 == 0) bn = 192; else bn = 256;
+  if (d.coutpad % bn == 0 && d.epilogue != RNC_EPI_RELU_FLOW && d.epilogue != RNC_EPI_FLOW_DELTA)
+    bn = choose_bn(d, bn, stride);
   if (d.coutpad % bn != 0 || d.coutpad < d.cout) return RNC_ERR_BAD_SHAPE;
   if (d.epilogue == RNC_EPI_RELU_FLOW && (d.coutpad < d.cout + 2 || !d.aux0 || !d.out_hi)) return RNC_ERR_BAD_SHAPE;
   if (d.out_hi && (!d.out_lo || (d.ldo_split & 7) || !aligned16(d.out_hi) || !aligned16(d.out_lo))) return RNC_ERR_BAD_POINTER;
@@ -487,6 +528,10 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   // Measured on B200: with 1024-byte-aligned stages the 128B swizzle is a function of the absolute shared-memory address,
   // so a descriptor whose start is shifted by kx rows (kx*128 B) needs NO base_offset; setting it breaks the result.
   p.use_base_offset = (d.flags & RNC_CONV_BASE_OFFSET) ? 1 : 0;
+  {
+    static const char* env = getenv("RNC_CONV_PROBE_NOB");
+    p.probe_nob = env != nullptr && env[0] == '1';
+  }
   p.tiles_x = (d.W + TW - 1) / TW; p.tiles_y = (d.H + TH - 1) / TH;
   p.ntiles = d.B * p.tiles_x * p.tiles_y; p.ntn = d.coutpad / bn;
   p.a_plane = box_w * box_h * 128;

@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import native
-from .engine import _ptr, _require_cuda, _stream, make_engine
+from .engine import _Timed, _ptr, _require_cuda, _stream, make_engine
 from .modules import BasicEncoder, BasicUpdateBlock, get_upsampler
 
 
@@ -82,8 +82,9 @@ class _RAFTBase(nn.Module):
         amp = bool(getattr(self.args, "mixed_precision", False))
         if eng.mode == "umma" and not amp and os.environ.get("RNC_ENCODER", "umma").lower() == "umma":
             # encoders on the tensor-core path, writing straight into the resident buffers (raft_nc_dbl.py:118-140)
-            eng.encoder().run(self, ws, image1.float().contiguous(), image2.float().contiguous())
-            eng.finish_fmaps(ws)
+            with _Timed(eng, "encoders"):
+                eng.encoder().run(self, ws, image1.float().contiguous(), image2.float().contiguous())
+                eng.finish_fmaps(ws)
         else:
             image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
             image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
