@@ -33,7 +33,7 @@ typedef enum {
 } rnc_status;
 
 /* Library identity / diagnostics. */
-int rnc_abi_version(void);                 /* bumps on any signature change */
+int rnc_abi_version(void);                 /* bumps on any signature change (now 4) */
 const char* rnc_build_info(void);          /* e.g. "sm_100a nvcc 12.9" */
 const char* rnc_status_string(int status);
 int rnc_last_cuda_error(void);             /* cudaError_t of the last failed launch on this thread */
@@ -206,6 +206,13 @@ int rnc_conv_flow7x7_split_fwd(const float* coords1, const float* weight, const 
  * in CL [B][H][W][cin]; weight packed [9][cin][2]; delta (optional, may be NULL) and coords1 NCHW [B][2][H][W]. */
 int rnc_flow_head2_fwd(const float* in, int cin, int ldi, const float* weight, const float* bias,
                        int B, int H, int W, float* delta, float* coords1, void* stream);
+
+/* FlowHead.conv2 (update.py:10,14), second half of the tensor-core formulation: `taps` [B*H*W][ldt] fp32 holds, for every
+ * pixel q, the 18 values W[o][:, ky, kx] . in[q] at column 2*(3*ky+kx)+o (a 1x1 convolution by rnc_conv2d_umma_fwd, K =
+ * cin instead of 9*cin); this sums the in-image 3x3 neighbours (zero padding), adds bias[2] (device), writes delta
+ * (optional, NCHW [B][2][H][W]) and does `coords1 = coords1 + delta_flow` (raft_nc_dbl.py:157). */
+int rnc_flow_tap_gather_fwd(const float* taps, int ldt, const float* bias, int B, int H, int W, float* delta, float* coords1,
+                            void* stream);
 
 /* coords_grid / initialize_flow (core/utils/utils.py:76-79, raft_nc_dbl.py:83-90) (+ optional flow_init, :144-145).
  * coords1 = grid (+ flow_init);  flow_init may be NULL. */

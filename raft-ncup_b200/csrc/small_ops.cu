@@ -202,6 +202,37 @@ convex_upsample_kernel(const float* __restrict__ flow, const float* __restrict__
   }
 }
 
+// FlowHead.conv2 as "1x1 conv per tap + shifted sum": P[q][2*tap + o] = W[o][:, tap] . in[q] was produced by a 1x1
+// tensor-core convolution (K = cin instead of 9*cin for two real output channels); the 3x3 convolution with zero padding is
+// out[o](y,x) = bias[o] + sum_tap P[(y+ky-1, x+kx-1)][2*tap + o] over the in-image neighbours.  Fused with
+// `coords1 = coords1 + delta_flow` (raft_nc_dbl.py:157).
+__global__ void flow_tap_gather_kernel(const float* __restrict__ P, int ldp, const float* __restrict__ bias, int B, int H, int W,
+                                       float* __restrict__ coords1, float* __restrict__ delta) {
+  const int HW = H * W;
+  const long long M = static_cast<long long>(B) * HW;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < M; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / HW), r = static_cast<int>(i - static_cast<long long>(b) * HW);
+    const int y = r / W, x = r - y * W;
+    float d0 = bias[0], d1 = bias[1];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + kx - 1;
+        if (xx < 0 || xx >= W) continue;
+        const float2 v = __ldg(reinterpret_cast<const float2*>(P + (static_cast<size_t>(b) * HW + yy * W + xx) * ldp + 2 * (ky * 3 + kx)));
+        d0 += v.x; d1 += v.y;
+      }
+    }
+    const size_t i0 = static_cast<size_t>(b) * 2 * HW + r;
+    coords1[i0] += d0;
+    coords1[i0 + HW] += d1;
+    if (delta) { delta[i0] = d0; delta[i0 + HW] = d1; }
+  }
+}
+
 }  // namespace rnc
 
 using namespace rnc;
@@ -236,6 +267,17 @@ int rnc_flow_head2_fwd(const float* in, int cin, int ldi, const float* weight, c
   if (blocks > 148 * 4) blocks = 148 * 4;
   const size_t smem = (size_t)9 * cin * 2 * sizeof(float);
   flow_head2_kernel<<<blocks, 256, smem, as_stream(stream)>>>(in, cin, ldi, weight, bias, B, H, W, delta, coords1);
+  return after_launch();
+}
+
+int rnc_flow_tap_gather_fwd(const float* taps, int ldt, const float* bias, int B, int H, int W, float* delta, float* coords1,
+                            void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0 || ldt < 18 || (ldt & 1)) return RNC_ERR_BAD_SHAPE;
+  if (!taps || !bias || !coords1 || (reinterpret_cast<uintptr_t>(taps) & 7)) return RNC_ERR_BAD_POINTER;
+  const long long M = static_cast<long long>(B) * H * W;
+  long long blocks = (M + 127) / 128;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  flow_tap_gather_kernel<<<static_cast<int>(blocks), 128, 0, as_stream(stream)>>>(taps, ldt, bias, B, H, W, coords1, delta);
   return after_launch();
 }
 

@@ -78,7 +78,11 @@ class PackedUpdateUmma:
         self.zr2 = UmmaWeights(cat([g.convz2.weight, g.convr2.weight], 0), cat([g.convz2.bias, g.convr2.bias], 0), [HX_LD])
         self.q2 = UmmaWeights(g.convq2.weight, g.convq2.bias, [128, 256])
         self.fh1 = UmmaWeights(fh.conv1.weight, fh.conv1.bias, [128])
-        self.fh2 = UmmaWeights(fh.conv2.weight, fh.conv2.bias, [256])      # Cout = 2 padded to a 32-wide N tile
+        # FlowHead.conv2 (3x3, 256 -> 2): as a 1x1 layer with one output pair per tap (18 -> 32 columns, K = 256 instead of
+        # 2304), summed over the shifted neighbours by rnc_flow_tap_gather_fwd
+        w2 = fh.conv2.weight.detach().float()                                # [2, 256, 3, 3]
+        self.fh2 = UmmaWeights(w2.permute(2, 3, 0, 1).reshape(18, w2.shape[1], 1, 1), None, [256])
+        self.fh2_bias = fh.conv2.bias.detach().float().contiguous()
         self.has_mask = len(ub.mask) > 0
         if self.has_mask:
             self.m0 = UmmaWeights(ub.mask[0].weight, ub.mask[0].bias, [128])
@@ -128,6 +132,7 @@ class UmmaWorkspace:
         self.h = torch.zeros(M, 128, **f)            # fp32 master copy of the GRU state
         self.z = torch.empty(M, 128, **f)
         self.fh = SplitBuf(M, 256, device)
+        self.fh2p = torch.empty(M, 32, **f)      # FlowHead.conv2 per-tap partial sums
         self.tmp = torch.empty(M, 256, **f)
         self.coords1 = torch.empty(B, 2, H8, W8, **f)
         self.delta = torch.empty(B, 2, H8, W8, **f)
@@ -295,8 +300,9 @@ class UmmaEngine(Engine):
                        out_split=ws.hx.ptrs(), ldo_split=HX_LD, h=hp, ldh=128, aux0=ws.z.data_ptr(), ldaux=128)
         # FlowHead (update.py:13-14) + coords1 += delta (raft_nc_dbl.py:157)
         self.uconv(B, H, W, ws.hx.ptrs(), 128, HX_LD, pk.fh1, E.EPI_RELU, out_split=ws.fh.ptrs(), ldo_split=256)
-        self.uconv(B, H, W, ws.fh.ptrs(), 256, 256, pk.fh2, E.EPI_FLOW_DELTA, aux0=ws.coords1.data_ptr(),
-                   out_f32=ws.delta.data_ptr() if want_delta else 0)
+        self.uconv(B, H, W, ws.fh.ptrs(), 256, 256, pk.fh2, E.EPI_LINEAR, out_f32=ws.fh2p.data_ptr(), ldo_f32=32)
+        native.check(self.L.rnc_flow_tap_gather_fwd(_ptr(ws.fh2p), 32, _ptr(pk.fh2_bias), B, H, W,
+                                                    _ptr(ws.delta) if want_delta else None, _ptr(ws.coords1), s), "flow_tap_gather")
         if want_mask:
             self.uconv(B, H, W, ws.hx.ptrs(), 128, HX_LD, pk.m0, E.EPI_RELU, out_split=ws.mh.ptrs(), ldo_split=256)
             self.uconv(B, H, W, ws.mh.ptrs(), 256, 256, pk.m2, E.EPI_LINEAR, out_f32=ws.mask.data_ptr(), ldo_f32=576)
