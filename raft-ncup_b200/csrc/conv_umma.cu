@@ -164,6 +164,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
     // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
     {
       const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(kBM >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | (static_cast<uint32_t>((2 * BN <= 256 ? 2 * BN : BN) >> 3) << 17) | (static_cast<uint32_t>(kBM >> 4) << 24);
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
       const int shift_rows = p.mode == MODE_ROWHALO ? 1 : p.mode == MODE_COLHALO ? p.TW : 0;
       int a_it = 0, b_it = 0, t_it = 0;
@@ -189,11 +190,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
               const uint32_t br = b_base + sb * 2 * C::kBTile;
               const uint64_t bh = smem_desc_sw128(br), bl = smem_desc_sw128(br + C::kBTile);
               if (elect_one()) {
+                if (BN <= 128) {
+                  // The hi and lo weight planes are adjacent in the stage and `main`, `corr` adjacent in TMEM, so
+                  // x_hi * [w_hi | w_lo] is ONE instruction of 2*BN columns: x_hi is fetched from shared memory once
+                  // instead of twice (a 128-column instruction needs the full 128 B/clk of shared-memory bandwidth).
 #pragma unroll
-                for (int k = 0; k < kBK / 16; ++k) {
-                  umma_f16(d_main, ah + 2 * k, bh + 2 * k, idesc, k == 0 ? acc : 1u);
-                  umma_f16(d_corr, ah + 2 * k, bl + 2 * k, idesc, k == 0 ? acc : 1u);
-                  umma_f16(d_corr, al + 2 * k, bh + 2 * k, idesc, 1);
+                  for (int k = 0; k < kBK / 16; ++k) {
+                    umma_f16(d_main, ah + 2 * k, bh + 2 * k, idesc2, k == 0 ? acc : 1u);
+                    umma_f16(d_corr, al + 2 * k, bh + 2 * k, idesc, 1);
+                  }
+                } else {
+#pragma unroll
+                  for (int k = 0; k < kBK / 16; ++k) {
+                    umma_f16(d_main, ah + 2 * k, bh + 2 * k, idesc, k == 0 ? acc : 1u);
+                    umma_f16(d_corr, ah + 2 * k, bl + 2 * k, idesc, k == 0 ? acc : 1u);
+                    umma_f16(d_corr, al + 2 * k, bh + 2 * k, idesc, 1);
+                  }
                 }
                 umma_commit(&b_empty[sb]);
               }
