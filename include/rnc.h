@@ -33,7 +33,7 @@ typedef enum {
 } rnc_status;
 
 /* Library identity / diagnostics. */
-int rnc_abi_version(void);                 /* bumps on any signature change (now 4) */
+int rnc_abi_version(void);                 /* bumps on any signature change (now 5) */
 const char* rnc_build_info(void);          /* e.g. "sm_100a nvcc 12.9" */
 const char* rnc_status_string(int status);
 int rnc_last_cuda_error(void);             /* cudaError_t of the last failed launch on this thread */
@@ -163,6 +163,8 @@ typedef struct {
   int hin, win;                        /* input height/width (0 -> same as H, W)                                    */
   const float* res; int ldres;         /* residual (fp32 CL at output resolution) for RELU_ADD_RELU                 */
   int flags;                           /* RNC_CONV_*                                                                 */
+  double* stats;                       /* optional (RNC_EPI_LINEAR + out_f32 only): [B][cout][2] sum / sum of squares of the
+                                        * outputs, ACCUMULATED (caller keeps it zeroed: rnc_instnorm_finalize re-zeroes) */
 } rnc_conv_umma_desc;
 
 int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream);
@@ -189,6 +191,9 @@ int rnc_stem_conv7x7s2_fwd(const float* img, const float* weight, const float* b
 /* nn.InstanceNorm2d (no affine, biased variance; extractor.py:28-33,128-129) statistics of x CL fp32 [N][P][C], C <= 128:
  * stats = fp64 scratch [N][C][2]; mean_rstd = [N][C][2] floats (mean, 1/sqrt(var+eps)). */
 int rnc_instnorm_stats(const float* x, int N, int P, int C, float eps, double* stats, float* mean_rstd, void* stream);
+/* Second half of rnc_instnorm_stats when the sums were accumulated elsewhere (rnc_conv_umma_desc.stats): stats [N][C][2]
+ * fp64 sums over P positions -> mean_rstd, then stats is zeroed for the next producer. */
+int rnc_instnorm_finalize(double* stats, int N, int P, int C, float eps, float* mean_rstd, void* stream);
 /* apply: mode 0: norm(x) -> out_f32;  1: relu(norm(x));  2: relu(res + relu(norm(x)))  (ResidualBlock.forward,
  * extractor.py:48-56); outputs fp32 and/or split halves, all CL [N][P][C]. */
 int rnc_instnorm_apply(const float* x, const float* mean_rstd, const float* res, int N, int P, int C, int mode,

@@ -42,6 +42,7 @@ struct Params {
   float* h; int ldh;
   float* aux0; int ldaux;
   const float* res; int ldres;
+  double* stats;                      // [B][cout][2]: per-(image, channel) sum / sum of squares of the outputs, accumulated
 };
 
 // K-major SW128 descriptor with a row shift inside the 8-row swizzle atom (base_offset = (addr >> 7) & 7)
@@ -61,6 +62,19 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   }
   hi = *reinterpret_cast<uint4*>(h);
   lo = *reinterpret_cast<uint4*>(l);
+}
+
+// Sum over the warp of v[j] per j, by halving exchanges (31 shuffles): on return lane l holds the total of element l in v[0].
+__device__ __forceinline__ void warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off], keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
 }
 
 template <int BN>
@@ -93,6 +107,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
   uint64_t* acc_full = b_empty + kMaxSB;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  double* stat_acc = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(bars) + 512);   // [8 warps][kHalfN][32 lanes][2], BN <= 128 only
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int items = p.ntiles * p.ntn;
@@ -224,10 +239,31 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
     const int lg = warp & 3;                       // TMEM lane group this warp may access
     const int ml = lg * 32 + lane;                 // row of the tile = pixel
     const int epi = p.epilogue;
+    constexpr int kChunksN = BN / 32, kHalfN = (kChunksN + 1) / 2;
+    const int cc0 = (warp - 2) < 4 ? 0 : kHalfN, cc1 = (warp - 2) < 4 ? kHalfN : kChunksN;
+    const bool use_stats = BN <= 128 && p.stats != nullptr;
+    double* my_acc = stat_acc + (static_cast<size_t>(warp - 2) * kHalfN * 32 + lane) * 2;   // [chunk] stride 64 doubles
+    int acc_b = -1, acc_n0 = 0;
+    auto flush_stats = [&]() {
+      if (acc_b < 0) return;
+      for (int ci = 0; ci < cc1 - cc0; ++ci) {
+        const int ch = acc_n0 + (cc0 + ci) * 32 + lane;
+        if (ch < p.cout) {
+          double* dst = p.stats + (static_cast<size_t>(acc_b) * p.cout + ch) * 2;
+          atomicAdd(dst, my_acc[ci * 64]);
+          atomicAdd(dst + 1, my_acc[ci * 64 + 1]);
+        }
+        my_acc[ci * 64] = 0.0; my_acc[ci * 64 + 1] = 0.0;
+      }
+    };
+    if (use_stats) {
+      for (int ci = 0; ci < kHalfN; ++ci) { my_acc[ci * 64] = 0.0; my_acc[ci * 64 + 1] = 0.0; }
+    }
     int t_it = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++t_it) {
       const int tile = item / p.ntn, n0 = (item - tile * p.ntn) * BN;
       const int b = tile / tpi, tr = tile - b * tpi;
+      if (use_stats && (b != acc_b || n0 != acc_n0)) { flush_stats(); acc_b = b; acc_n0 = n0; }
       const int y = (tr / p.tiles_x) * p.TH + ml / p.TW, x = (tr % p.tiles_x) * p.TW + ml % p.TW;
       const bool valid = y < p.H && x < p.W;
       const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
@@ -235,8 +271,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
       mbar_wait(&acc_full[buf], use & 1);
       tcgen05_fence_after();
       // two epilogue warps per TMEM lane group: the first takes the lower half of the 32-channel chunks, the second the rest
-      constexpr int kChunksN = BN / 32, kHalfN = (kChunksN + 1) / 2;
-      const int cc0 = (warp - 2) < 4 ? 0 : kHalfN, cc1 = (warp - 2) < 4 ? kHalfN : kChunksN;
 #pragma unroll 1
       for (int cc = cc0; cc < cc1; ++cc) {
         const int n = n0 + cc * 32;
@@ -245,7 +279,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + buf * 2 * BN + cc * 32;
         tmem_ld32(taddr, r);
         tmem_ld32(taddr + BN, rc);
-        if (!valid) continue;
+        if (!valid && !use_stats) continue;
         float v[32];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -254,6 +288,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
           v[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]) + __uint_as_float(rc[4 * q + 1]), p.unscale, bv.y);
           v[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]) + __uint_as_float(rc[4 * q + 2]), p.unscale, bv.z);
           v[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]) + __uint_as_float(rc[4 * q + 3]), p.unscale, bv.w);
+        }
+        if (use_stats) {
+          // InstanceNorm statistics of this layer's output (extractor.py:128-129), fused here instead of a pass over the
+          // fp32 tensor: fp32 partial sums over the warp's 32 pixels, accumulated in fp64 per lane (= channel) in shared
+          // memory across the CTA's tiles and flushed with fp64 atomics when the image changes
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { s1[j] = valid ? v[j] : 0.f; s2[j] = s1[j] * s1[j]; }
+          warp_transpose_sum(s1, lane);
+          warp_transpose_sum(s2, lane);
+          my_acc[(cc - cc0) * 64] += static_cast<double>(s1[0]);
+          my_acc[(cc - cc0) * 64 + 1] += static_cast<double>(s2[0]);
+          if (!valid) continue;
         }
         if (epi == RNC_EPI_GRU_ZR) {
           const int Ch = p.cout >> 1;
@@ -363,6 +410,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
+    if (use_stats) flush_stats();
   }
 
   // ------------------------------------------------------------------ teardown
@@ -420,7 +468,7 @@ static int launch(const CUtensorMap* maps, Params& p, cudaStream_t stream, int m
   p.SB = sb > kMaxSB ? kMaxSB : sb < 2 ? 2 : sb;
   if (max_sa > 0 && p.SA > max_sa) p.SA = max_sa;      // debug knobs (rnc_conv_umma_desc.flags bits 8-15)
   if (max_sb > 0 && p.SB > max_sb) p.SB = max_sb;
-  const int smem = p.SA * a_stage + p.SB * 2 * C::kBTile + 1024 + 512;
+  const int smem = p.SA * a_stage + p.SB * 2 * C::kBTile + 1024 + 512 + (BN <= 128 ? 8192 : 0);   // + fp64 statistics slots
   static unsigned long long done = 0;
   if (int st = ensure_dyn_smem(conv_umma_kernel<BN>, 227 * 1024, &done)) return st;
   const int items = p.ntiles * p.ntn;
@@ -492,6 +540,7 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   if (d.epilogue == RNC_EPI_RELU_FLOW && (d.coutpad < d.cout + 2 || !d.aux0 || !d.out_hi)) return RNC_ERR_BAD_SHAPE;
   if (d.out_hi && (!d.out_lo || (d.ldo_split & 7) || !aligned16(d.out_hi) || !aligned16(d.out_lo))) return RNC_ERR_BAD_POINTER;
   if (d.out_f32 && ((d.ldo_f32 & 3) || !aligned16(d.out_f32))) return RNC_ERR_BAD_POINTER;
+  if (d.stats && (d.epilogue != RNC_EPI_LINEAR || !d.out_f32 || d.coutpad > 128)) return RNC_ERR_UNSUPPORTED;
   switch (d.epilogue) {
     case RNC_EPI_RELU_ADD_RELU:
       if (!d.res || (d.ldres & 3) || !aligned16(d.res)) return RNC_ERR_BAD_POINTER;
@@ -552,6 +601,7 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   p.out_f32 = d.out_f32; p.ldo_f32 = d.ldo_f32;
   p.out_hi = static_cast<__half*>(d.out_hi); p.out_lo = static_cast<__half*>(d.out_lo); p.ldo_split = d.ldo_split;
   p.h = d.h; p.ldh = d.ldh; p.aux0 = d.aux0; p.ldaux = d.ldaux; p.res = d.res; p.ldres = d.ldres;
+  p.stats = d.stats;
 
   CUtensorMap maps[6];
   bool ok = make_in_map(&maps[0], d.in0_hi, d.c0, d.ld0, d.B, Hin, Win, box_w, box_h, stride) &&

@@ -143,13 +143,14 @@ instnorm_stats_kernel(const float* __restrict__ x, int P, int C, int rows_per_ct
   }
 }
 
-__global__ void instnorm_finalize_kernel(const double* __restrict__ stats, int NC, int P, float eps, float* __restrict__ mean_rstd) {
+__global__ void instnorm_finalize_kernel(double* __restrict__ stats, int NC, int P, float eps, float* __restrict__ mean_rstd, int rezero) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= NC) return;
   const double mean = stats[2 * i] / P;
   const double var = fmax(stats[2 * i + 1] / P - mean * mean, 0.0);     // biased variance (F.instance_norm)
   mean_rstd[2 * i] = (float)mean;
   mean_rstd[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  if (rezero) { stats[2 * i] = 0.0; stats[2 * i + 1] = 0.0; }           // ready for the next accumulating producer
 }
 
 // ---------------------------------------------------------------- instance norm apply (+ ReLU / residual / split)
@@ -256,7 +257,14 @@ int rnc_instnorm_stats(const float* x, int N, int P, int C, float eps, double* s
   dim3 grid((P + rows - 1) / rows, N);
   instnorm_stats_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, P, C, rows, stats);
   if (int st = after_launch()) return st;
-  instnorm_finalize_kernel<<<(N * C + 127) / 128, 128, 0, as_stream(stream)>>>(stats, N * C, P, eps, mean_rstd);
+  instnorm_finalize_kernel<<<(N * C + 127) / 128, 128, 0, as_stream(stream)>>>(stats, N * C, P, eps, mean_rstd, 1);
+  return after_launch();
+}
+
+int rnc_instnorm_finalize(double* stats, int N, int P, int C, float eps, float* mean_rstd, void* stream) {
+  if (N <= 0 || P <= 0 || C <= 0) return RNC_ERR_BAD_SHAPE;
+  if (!stats || !mean_rstd) return RNC_ERR_BAD_POINTER;
+  instnorm_finalize_kernel<<<(N * C + 127) / 128, 128, 0, as_stream(stream)>>>(stats, N * C, P, eps, mean_rstd, 1);
   return after_launch();
 }
 

@@ -71,7 +71,7 @@ class EncoderBuffers:
             self.D32.append(torch.empty(rows, c, **f) if c != 64 else None)
             self.XS.append(SplitBuf(rows, c, device))
             self.AS.append(SplitBuf(rows, c, device))
-        self.stats = torch.empty(N * 128 * 2, dtype=torch.float64, device=device)
+        self.stats = torch.zeros(N * 128 * 2, dtype=torch.float64, device=device)   # kept zeroed by rnc_instnorm_finalize
         self.mr = torch.empty(N * 128 * 2, **f)
 
 
@@ -98,9 +98,13 @@ class EncoderRunner:
         return self._bufs
 
     # ------------------------------------------------------------------ instance-norm helpers
-    def _norm(self, bufs, x32, N, P, Cc, mode, res=None, out32=None, split=None):
+    def _norm(self, bufs, x32, N, P, Cc, mode, res=None, out32=None, split=None, fused_stats=False):
+        """fused_stats: the producing convolution already accumulated the sums into bufs.stats (rnc_conv_umma_desc.stats)."""
         s = _stream()
-        native.check(self.L.rnc_instnorm_stats(_ptr(x32), N, P, Cc, EPS, _ptr(bufs.stats), _ptr(bufs.mr), s), "instnorm_stats")
+        if fused_stats:
+            native.check(self.L.rnc_instnorm_finalize(_ptr(bufs.stats), N, P, Cc, EPS, _ptr(bufs.mr), s), "instnorm_finalize")
+        else:
+            native.check(self.L.rnc_instnorm_stats(_ptr(x32), N, P, Cc, EPS, _ptr(bufs.stats), _ptr(bufs.mr), s), "instnorm_stats")
         native.check(self.L.rnc_instnorm_apply(_ptr(x32), _ptr(bufs.mr), _ptr(res), N, P, Cc, mode, _ptr(out32),
                                                C.c_void_p(split.hi.data_ptr() if split else 0),
                                                C.c_void_p(split.lo.data_ptr() if split else 0), s), "instnorm_apply")
@@ -127,17 +131,19 @@ class EncoderRunner:
             P = h * w
             xs_in, x32_in = bufs.XS[src], bufs.X32[src]
             if inst:
+                st = bufs.stats.data_ptr()
                 eng.uconv(N, h, w, xs_in.ptrs(), cin, cin, w1, E.EPI_LINEAR, out_f32=bufs.T32[lvl].data_ptr(), ldo_f32=cout,
-                          stride=stride, hin=hi_, win=wi_)
-                self._norm(bufs, bufs.T32[lvl], N, P, cout, 1, split=bufs.AS[lvl])
+                          stride=stride, hin=hi_, win=wi_, stats=st)
+                self._norm(bufs, bufs.T32[lvl], N, P, cout, 1, split=bufs.AS[lvl], fused_stats=True)
                 res = x32_in
                 if wd is not None:
                     eng.uconv(N, h, w, xs_in.ptrs(), cin, cin, wd, E.EPI_LINEAR, out_f32=bufs.T32[lvl].data_ptr(), ldo_f32=cout,
-                              stride=stride, hin=hi_, win=wi_)
-                    self._norm(bufs, bufs.T32[lvl], N, P, cout, 0, out32=bufs.D32[lvl])
+                              stride=stride, hin=hi_, win=wi_, stats=st)
+                    self._norm(bufs, bufs.T32[lvl], N, P, cout, 0, out32=bufs.D32[lvl], fused_stats=True)
                     res = bufs.D32[lvl]
-                eng.uconv(N, h, w, bufs.AS[lvl].ptrs(), cout, cout, w2, E.EPI_LINEAR, out_f32=bufs.T32[lvl].data_ptr(), ldo_f32=cout)
-                self._norm(bufs, bufs.T32[lvl], N, P, cout, 2, res=res, out32=bufs.X32[lvl], split=bufs.XS[lvl])
+                eng.uconv(N, h, w, bufs.AS[lvl].ptrs(), cout, cout, w2, E.EPI_LINEAR, out_f32=bufs.T32[lvl].data_ptr(), ldo_f32=cout,
+                          stats=st)
+                self._norm(bufs, bufs.T32[lvl], N, P, cout, 2, res=res, out32=bufs.X32[lvl], split=bufs.XS[lvl], fused_stats=True)
             else:
                 eng.uconv(N, h, w, xs_in.ptrs(), cin, cin, w1, E.EPI_RELU, out_split=bufs.AS[lvl].ptrs(), ldo_split=cout,
                           stride=stride, hin=hi_, win=wi_)

@@ -10,7 +10,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librnc.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 (EPI_LINEAR, EPI_RELU, EPI_SIGMOID, EPI_GRU_ZR, EPI_GRU_Q, EPI_RELU_FLOW, EPI_RELU_ADD_RELU, EPI_TANH_RELU,
  EPI_FLOW_DELTA) = range(9)
@@ -52,7 +52,7 @@ class UmmaConvDesc(C.Structure):
                 ("B", _i), ("H", _i), ("W", _i),
                 ("cout", _i), ("kh", _i), ("kw", _i), ("epilogue", _i),
                 ("stride", _i), ("hin", _i), ("win", _i),
-                ("res", _vp), ("ldres", _i), ("flags", _i)]
+                ("res", _vp), ("ldres", _i), ("flags", _i), ("stats", _vp)]
 
 
 # name -> (restype, argtypes); every symbol include/rnc.h declares
@@ -75,6 +75,7 @@ SIGNATURES = {
     "rnc_f32_to_split": (_i, [_vp, _i, _i, C.c_longlong, _vp, _vp, _i, _i, _vp]),
     "rnc_stem_conv7x7s2_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "rnc_instnorm_stats": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "rnc_instnorm_finalize": (_i, [_vp, _i, _i, _i, _f, _vp, _vp]),
     "rnc_instnorm_apply": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "rnc_add_relu_split": (_i, [_vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp]),
     "rnc_fmap_pyramid": (_i, [_vp, _i, _i, _i, _i, _i, _vp]),
