@@ -280,8 +280,8 @@ def run_native(args, rank, world, local_rank):
                      "avg_launch_ms": k2_ms, "launches_timed": len(prof.get("corr_lookup", [])),
                      "isolated": {"avg_launch_ms": iso_ms, "achieved": (k2_bytes / (iso_ms * 1e-3) / 1e9) if iso_ms else None,
                                   "frac": (k2_bytes / (iso_ms * 1e-3) / 1e9 / peak) if iso_ms else None,
-                                  "note": "same kernel, 32 back-to-back launches with nothing co-scheduled; in the timed region "
-                                          "the CUDA-core convf1 kernel shares the SMs with it on a side stream"}},
+                                  "note": "same kernel, 32 back-to-back launches outside the timed region (warm L2, no "
+                                          "neighbouring kernels)"}},
         "roofline_ncup": {"kernel": "ncup_fused_kernel (K4)", "bound": "hbm", "achieved": k4_gbs, "peak": peak, "unit": "GB/s",
                           "frac": k4_gbs / peak, "avg_launch_ms": k4_ms,
                           "algorithmic_bytes_per_launch": K4_BYTES_PER_PAIR_CALL * args.batch},

@@ -33,7 +33,7 @@ typedef enum {
 } rnc_status;
 
 /* Library identity / diagnostics. */
-int rnc_abi_version(void);                 /* bumps on any signature change (now 5) */
+int rnc_abi_version(void);                 /* bumps on any signature change (now 6) */
 const char* rnc_build_info(void);          /* e.g. "sm_100a nvcc 12.9" */
 const char* rnc_status_string(int status);
 int rnc_last_cuda_error(void);             /* cudaError_t of the last failed launch on this thread */
@@ -211,6 +211,11 @@ int rnc_conv_flow7x7_split_fwd(const float* coords1, const float* weight, const 
  * in CL [B][H][W][cin]; weight packed [9][cin][2]; delta (optional, may be NULL) and coords1 NCHW [B][2][H][W]. */
 int rnc_flow_head2_fwd(const float* in, int cin, int ldi, const float* weight, const float* bias,
                        int B, int H, int W, float* delta, float* coords1, void* stream);
+
+/* convf1 = Conv2d(2,128,7,padding=3) on flow = coords1 - grid (update.py:83,93-94), first half of the tensor-core
+ * formulation: writes, for every pixel, its zero-padded 7x7x2 flow neighbourhood as 98 (+30 zero) split halves,
+ * column k = 2*(7*ky+kx)+c, rows of ld >= 128 halves; a 1x1 rnc_conv2d_umma_fwd with the [128][98] weight finishes it. */
+int rnc_flow_im2col7_split_fwd(const float* coords1, int B, int H, int W, void* out_hi, void* out_lo, int ld, void* stream);
 
 /* FlowHead.conv2 (update.py:10,14), second half of the tensor-core formulation: `taps` [B*H*W][ldt] fp32 holds, for every
  * pixel q, the 18 values W[o][:, ky, kx] . in[q] at column 2*(3*ky+kx)+o (a 1x1 convolution by rnc_conv2d_umma_fwd, K =

@@ -233,6 +233,42 @@ __global__ void flow_tap_gather_kernel(const float* __restrict__ P, int ldp, con
   }
 }
 
+// convf1 = Conv2d(2, 128, 7, padding=3) on flow = coords1 - grid (update.py:83,93-94), first half of the tensor-core
+// formulation: the 7x7x2 neighbourhood of every pixel as one K-major row of 98 (+30 zero) split halves, k = 2*(7*ky+kx)+c,
+// which a 1x1 tensor-core layer then multiplies by the [128][98] weight.  One thread = one pixel x 8 consecutive k.
+__global__ void flow_im2col7_kernel(const float* __restrict__ coords1, int B, int H, int W, __half* __restrict__ out_hi,
+                                    __half* __restrict__ out_lo, int ld) {
+  const int HW = H * W;
+  const long long total = static_cast<long long>(B) * HW * 16;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i & 15);
+    const long long pix = i >> 4;
+    const int b = static_cast<int>(pix / HW), r = static_cast<int>(pix - static_cast<long long>(b) * HW);
+    const int y = r / W, x = r - y * W;
+    const float* cx = coords1 + static_cast<size_t>(b) * 2 * HW;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int tap = g * 4 + j;                 // 4 taps x 2 components per thread
+      const int ky = tap / 7, kx = tap - ky * 7;
+      const int yy = y + ky - 3, xx = x + kx - 3;
+      const bool in = tap < 49 && yy >= 0 && yy < H && xx >= 0 && xx < W;
+      v[2 * j] = in ? __ldg(cx + yy * W + xx) - static_cast<float>(xx) : 0.f;
+      v[2 * j + 1] = in ? __ldg(cx + HW + yy * W + xx) - static_cast<float>(yy) : 0.f;
+    }
+    __half2 hh[4], ll[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = fminf(fmaxf(v[2 * j], -65504.f), 65504.f), c = fminf(fmaxf(v[2 * j + 1], -65504.f), 65504.f);
+      hh[j] = __floats2half2_rn(a, c);
+      const float2 back = __half22float2(hh[j]);
+      ll[j] = __floats2half2_rn(a - back.x, c - back.y);
+    }
+    *reinterpret_cast<uint4*>(out_hi + pix * ld + g * 8) = *reinterpret_cast<uint4*>(hh);
+    *reinterpret_cast<uint4*>(out_lo + pix * ld + g * 8) = *reinterpret_cast<uint4*>(ll);
+  }
+}
+
 }  // namespace rnc
 
 using namespace rnc;
@@ -267,6 +303,17 @@ int rnc_flow_head2_fwd(const float* in, int cin, int ldi, const float* weight, c
   if (blocks > 148 * 4) blocks = 148 * 4;
   const size_t smem = (size_t)9 * cin * 2 * sizeof(float);
   flow_head2_kernel<<<blocks, 256, smem, as_stream(stream)>>>(in, cin, ldi, weight, bias, B, H, W, delta, coords1);
+  return after_launch();
+}
+
+int rnc_flow_im2col7_split_fwd(const float* coords1, int B, int H, int W, void* out_hi, void* out_lo, int ld, void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0 || ld < 128 || (ld & 7)) return RNC_ERR_BAD_SHAPE;
+  if (!coords1 || !out_hi || !out_lo || !aligned16(out_hi) || !aligned16(out_lo)) return RNC_ERR_BAD_POINTER;
+  const long long total = static_cast<long long>(B) * H * W * 16;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  flow_im2col7_kernel<<<static_cast<int>(blocks), 256, 0, as_stream(stream)>>>(coords1, B, H, W, static_cast<__half*>(out_hi),
+                                                                              static_cast<__half*>(out_lo), ld);
   return after_launch();
 }
 

@@ -70,7 +70,10 @@ class PackedUpdateUmma:
         cat = torch.cat
         self.convc1 = UmmaWeights(expand_corr_weight(e.convc1.weight), e.convc1.bias, [CORR_LD])
         self.convc2 = UmmaWeights(e.convc2.weight, e.convc2.bias, [256])
-        self.convf1 = (pack_thin(e.convf1.weight), e.convf1.bias.detach().float().contiguous())
+        self.convf1 = (pack_thin(e.convf1.weight), e.convf1.bias.detach().float().contiguous())    # CUDA-core form (RNC_CONVF1=ffma)
+        # convf1 (7x7, 2 -> 128) as a 1x1 layer over the im2col'ed flow neighbourhood: k = 2*(7*ky+kx)+c, K = 98 (+30)
+        wf = e.convf1.weight.detach().float()
+        self.convf1_mm = UmmaWeights(wf.permute(0, 2, 3, 1).reshape(wf.shape[0], 98, 1, 1), e.convf1.bias, [98])
         self.convf2 = UmmaWeights(e.convf2.weight, e.convf2.bias, [128])
         self.conv = UmmaWeights(e.conv.weight, e.conv.bias, [256], extra_cout=2)
         self.zr1 = UmmaWeights(cat([g.convz1.weight, g.convr1.weight], 0), cat([g.convz1.bias, g.convr1.bias], 0), [HX_LD])
@@ -127,6 +130,7 @@ class UmmaWorkspace:
         self.c1 = SplitBuf(M, 256, device)
         self.corflo = SplitBuf(M, 256, device)
         self.f1 = SplitBuf(M, 128, device)
+        self.fcol = SplitBuf(M, 128, device)     # im2col of the flow for convf1
         self.hx = SplitBuf(M, HX_LD, device)
         self.rh = SplitBuf(M, 128, device)
         self.h = torch.zeros(M, 128, **f)            # fp32 master copy of the GRU state
@@ -162,7 +166,12 @@ class UmmaEngine(Engine):
             raise ValueError(f"RNC_LOOKUP={self.lookup_mode!r}: expected 'umma' or 'ffma'")
         # RNC_CONV_FLAGS: bit 0 = one A tile per tap (no halo sharing), bit 1 = no descriptor base_offset (debug)
         self.conv_flags = int(os.environ.get("RNC_CONV_FLAGS", "0"))
-        self.fork_convf1 = os.environ.get("RNC_FORK", "1") != "0"
+        # RNC_CONVF1=mm (default): convf1 as flow im2col + 1x1 tensor-core layer on the main stream; ffma: the CUDA-core 7x7
+        # kernel, forked onto a side stream underneath the lookup (RNC_FORK=0 keeps it on the main stream)
+        self.convf1_mode = os.environ.get("RNC_CONVF1", "mm").lower()
+        if self.convf1_mode not in ("mm", "ffma"):
+            raise ValueError(f"RNC_CONVF1={self.convf1_mode!r}: expected 'mm' or 'ffma'")
+        self.fork_convf1 = self.convf1_mode == "ffma" and os.environ.get("RNC_FORK", "1") != "0"
         self._side = None
 
     def packed_update(self, ub):
@@ -261,6 +270,11 @@ class UmmaEngine(Engine):
                                                           _stream()), "corr_lookup_split")
 
     def _convf1(self, ws, pk):
+        if self.convf1_mode == "mm":
+            native.check(self.L.rnc_flow_im2col7_split_fwd(_ptr(ws.coords1), ws.B, ws.H8, ws.W8, _ptr(ws.fcol.hi), _ptr(ws.fcol.lo), 128,
+                                                           _stream()), "flow_im2col7")
+            self.uconv(ws.B, ws.H8, ws.W8, ws.fcol.ptrs(), 98, 128, pk.convf1_mm, native.EPI_RELU, out_split=ws.f1.ptrs(), ldo_split=128)
+            return
         native.check(self.L.rnc_conv_flow7x7_split_fwd(_ptr(ws.coords1), _ptr(pk.convf1[0]), _ptr(pk.convf1[1]), ws.B, ws.H8, ws.W8,
                                                        128, _ptr(ws.f1.hi), _ptr(ws.f1.lo), 128, _stream()), "convf1")
 

@@ -77,6 +77,69 @@ def test_umma_conv_matches_fp32(ueng, cin, cout, kh, kw, act, W):
     assert (rec - out[:, :cout]).abs().max().item() < 1e-6 * scale + 1e-7
 
 
+@pytest.mark.parametrize("cout,W", [(64, 150), (96, 40), (128, 21)])
+def test_umma_conv_fused_instance_norm_statistics(ueng, cout, W):
+    """rnc_conv_umma_desc.stats + rnc_instnorm_finalize == InstanceNorm2d statistics of the layer's output
+    (extractor.py:128-129): ragged tiles, several images per CTA, accumulate-and-rezero protocol."""
+    import ctypes as C
+    from rnc import native
+    from rnc.engine_umma import SplitBuf, UmmaWeights
+    g = torch.Generator().manual_seed(cout + W)
+    B, H, cin = 3, 11, 64
+    x = torch.randn(B, cin, H, W, generator=g) + 0.5
+    w = torch.randn(cout, cin, 3, 3, generator=g) / 24.0
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    buf = SplitBuf(B * H * W, cin, DEV)
+    buf.hi[:], buf.lo[:] = split(x.permute(0, 2, 3, 1).reshape(-1, cin).to(DEV))
+    wt = UmmaWeights(w.to(DEV), b.to(DEV), [cin])
+    out = torch.zeros(B * H * W, wt.coutpad, device=DEV)
+    stats = torch.zeros(B * cout * 2, dtype=torch.float64, device=DEV)
+    mr = torch.zeros(B * cout * 2, device=DEV)
+    for _ in range(2):                                     # second round checks that finalize left the sums zeroed
+        ueng.uconv(B, H, W, buf.ptrs(), cin, cin, wt, native.EPI_LINEAR, out_f32=out.data_ptr(), ldo_f32=wt.coutpad,
+                   stats=stats.data_ptr())
+        native.check(ueng.L.rnc_instnorm_finalize(C.c_void_p(stats.data_ptr()), B, H * W, cout, 1e-5, C.c_void_p(mr.data_ptr()),
+                                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)), "finalize")
+        torch.cuda.synchronize()
+        assert stats.abs().max().item() == 0.0
+        got = mr.view(B, cout, 2).cpu()
+        mean = ref.mean(dim=(2, 3))
+        rstd = 1.0 / torch.sqrt(ref.var(dim=(2, 3), unbiased=False) + 1e-5)
+        assert (got[..., 0] - mean.float()).abs().max() < 2e-5 * max(1.0, mean.abs().max().item())
+        assert ((got[..., 1] - rstd.float()) / rstd.float()).abs().max() < 5e-5
+
+
+def test_flow_head_conv2_as_taps_plus_gather(ueng):
+    """FlowHead.conv2 (update.py:10,14) = 1x1 tensor-core layer over the 9 taps + rnc_flow_tap_gather_fwd, with
+    `coords1 += delta_flow` (raft_nc_dbl.py:157); borders exercise the zero padding."""
+    import ctypes as C
+    from rnc import native
+    from rnc.engine_umma import SplitBuf, UmmaWeights
+    g = torch.Generator().manual_seed(11)
+    B, H, W, cin = 2, 9, 37, 256
+    x = torch.relu(torch.randn(B, cin, H, W, generator=g))
+    w = torch.randn(2, cin, 3, 3, generator=g) / 48.0
+    b = torch.randn(2, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1).float()
+    buf = SplitBuf(B * H * W, cin, DEV)
+    buf.hi[:], buf.lo[:] = split(x.permute(0, 2, 3, 1).reshape(-1, cin).to(DEV))
+    wt = UmmaWeights(w.permute(2, 3, 0, 1).reshape(18, cin, 1, 1).to(DEV), None, [cin])
+    taps = torch.zeros(B * H * W, 32, device=DEV)
+    ueng.uconv(B, H, W, buf.ptrs(), cin, cin, wt, native.EPI_LINEAR, out_f32=taps.data_ptr(), ldo_f32=32)
+    coords = torch.randn(B, 2, H, W, generator=g).to(DEV)
+    c0 = coords.clone()
+    delta = torch.zeros(B, 2, H, W, device=DEV)
+    vp = C.c_void_p
+    bd = b.to(DEV)
+    native.check(ueng.L.rnc_flow_tap_gather_fwd(vp(taps.data_ptr()), 32, vp(bd.data_ptr()), B, H, W, vp(delta.data_ptr()),
+                                                vp(coords.data_ptr()), vp(torch.cuda.current_stream().cuda_stream)), "gather")
+    torch.cuda.synchronize()
+    assert (delta.cpu() - ref).abs().max() < 2e-5 * max(1.0, ref.abs().max().item())
+    assert (coords - (c0 + delta)).abs().max().item() < 1e-6
+    assert ueng.L.rnc_flow_tap_gather_fwd(vp(taps.data_ptr()), 16, vp(0), B, H, W, None, vp(coords.data_ptr()), None) != 0
+
+
 def test_umma_two_segment_input(ueng):
     # q-gate convolution: input = cat(r*h [128], x [256]) read from two buffers (update.py:49)
     from rnc import native
