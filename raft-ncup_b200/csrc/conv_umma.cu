@@ -109,6 +109,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   double* stat_acc = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(bars) + 512);   // [8 warps][kHalfN][32 lanes][2], BN <= 128 only
 
+  pdl_trigger();                       // the next kernel in the stream may begin its prologue on SMs this grid has left
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int items = p.ntiles * p.ntn;
   const int tpi = p.tiles_x * p.tiles_y;
@@ -126,6 +127,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                          // everything above overlapped the predecessor's tail; its results are visible from here
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -473,7 +475,9 @@ static int launch(const CUtensorMap* maps, Params& p, cudaStream_t stream, int m
   if (int st = ensure_dyn_smem(conv_umma_kernel<BN>, 227 * 1024, &done)) return st;
   const int items = p.ntiles * p.ntn;
   const int grid = items < sm_count() ? items : sm_count();
-  conv_umma_kernel<BN><<<grid, kThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  cudaError_t e = launch_pdl(conv_umma_kernel<BN>, dim3(grid), dim3(kThreads), smem, stream, maps[0], maps[1], maps[2], maps[3], maps[4],
+                             maps[5], p);
+  if (e != cudaSuccess) { g_last_cuda_error = static_cast<int>(e); return RNC_ERR_CUDA; }
   return after_launch();
 }
 

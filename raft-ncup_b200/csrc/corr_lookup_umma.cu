@@ -312,6 +312,7 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ti_empty + kTiRing);
   TileInfo* ti = reinterpret_cast<TileInfo*>(tmem_slot + 2);  // [kTiRing]
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tpi = p.tiles_x * p.tiles_y;
   const int ntiles = p.B * tpi;
@@ -329,6 +330,7 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                          // coords1 of the previous iteration's flow update is visible from here
 
   const int nunits = ntiles * kLevels;
   const int tm = p.tile_major;
@@ -668,7 +670,9 @@ extern "C" int rnc_corr_lookup_umma_fwd(const void* f1h_cl, const void* f2h_pyr,
   if (int st = ensure_dyn_smem(corr_lookup_umma_kernel, kSmemTotal, &done)) return st;
   const int ntiles = B * p.tiles_x * p.tiles_y;
   const int grid = ntiles * kLevels < sm_count() ? ntiles * kLevels : sm_count();   // persistent: one CTA per SM
-  corr_lookup_umma_kernel<<<grid, kThreads, kSmemTotal, as_stream(stream)>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  cudaError_t e = launch_pdl(corr_lookup_umma_kernel, dim3(grid), dim3(kThreads), kSmemTotal, as_stream(stream), maps[0], maps[1], maps[2],
+                             maps[3], maps[4], p);
+  if (e != cudaSuccess) { g_last_cuda_error = static_cast<int>(e); return RNC_ERR_CUDA; }
   if (int st = after_launch()) return st;
   // exact recomputation of the tiles the fixed boxes could not cover
   return rnc_corr_lookup_fallback_split(f1_cl, f2_pyr, coords, B, D, H, W, levels, out_hi, out_lo, ldo, lvl_stride, p.flags,

@@ -144,6 +144,7 @@ instnorm_stats_kernel(const float* __restrict__ x, int P, int C, int rows_per_ct
 }
 
 __global__ void instnorm_finalize_kernel(double* __restrict__ stats, int NC, int P, float eps, float* __restrict__ mean_rstd, int rezero) {
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= NC) return;
   const double mean = stats[2 * i] / P;
@@ -160,6 +161,7 @@ __global__ void instnorm_finalize_kernel(double* __restrict__ stats, int NC, int
 __global__ void instnorm_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean_rstd, const float* __restrict__ res,
                                       int N, int P, int C, int mode, float* __restrict__ out_f32,
                                       __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  pdl_trigger();
   const int c4 = C >> 2;
   const size_t total = (size_t)N * P * c4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {

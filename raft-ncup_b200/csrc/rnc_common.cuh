@@ -1,5 +1,6 @@
 // Shared helpers for the rnc kernels (sm_100a only).
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "rnc.h"
@@ -41,6 +42,29 @@ inline int after_launch(int n = 1) {
 }
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Programmatic dependent launch (PDL).  A kernel launched with launch_pdl() may start while its predecessor in the stream is
+// still draining: it runs its prologue (barrier init, TMEM allocation, descriptor prefetch), then pdl_wait() blocks until the
+// predecessor has completed and its writes are visible.  pdl_trigger() in the predecessor lets the dependent start early;
+// without it the dependent starts at the predecessor's exit (plain stream order).  RNC_PDL=0 disables the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static const int on = [] { const char* e = getenv("RNC_PDL"); return (e && e[0] == '0') ? 0 : 1; }();
+  return on != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 

@@ -208,6 +208,7 @@ convex_upsample_kernel(const float* __restrict__ flow, const float* __restrict__
 // `coords1 = coords1 + delta_flow` (raft_nc_dbl.py:157).
 __global__ void flow_tap_gather_kernel(const float* __restrict__ P, int ldp, const float* __restrict__ bias, int B, int H, int W,
                                        float* __restrict__ coords1, float* __restrict__ delta) {
+  pdl_trigger();
   const int HW = H * W;
   const long long M = static_cast<long long>(B) * HW;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < M; i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -238,6 +239,7 @@ __global__ void flow_tap_gather_kernel(const float* __restrict__ P, int ldp, con
 // which a 1x1 tensor-core layer then multiplies by the [128][98] weight.  One thread = one pixel x 8 consecutive k.
 __global__ void flow_im2col7_kernel(const float* __restrict__ coords1, int B, int H, int W, __half* __restrict__ out_hi,
                                     __half* __restrict__ out_lo, int ld) {
+  pdl_trigger();
   const int HW = H * W;
   const long long total = static_cast<long long>(B) * HW * 16;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
