@@ -52,16 +52,11 @@ __device__ __forceinline__ uint64_t smem_desc_sw128_shift(uint32_t saddr) {
 
 // exact hi/lo split of 8 floats into two 16-byte vectors of halves
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
-  __half2 h[4], l[4];
+  uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float a = fminf(fmaxf(v[2 * i], -65504.f), 65504.f), b = fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f);
-    const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
-    h[i] = __halves2half2(ha, hb);
-    l[i] = __halves2half2(__float2half_rn(a - __half2float(ha)), __float2half_rn(b - __half2float(hb)));
-  }
-  hi = *reinterpret_cast<uint4*>(h);
-  lo = *reinterpret_cast<uint4*>(l);
+  for (int i = 0; i < 4; ++i) split_pair(v[2 * i], v[2 * i + 1], h[i], l[i]);
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // Sum over the warp of v[j] per j, by halving exchanges (31 shuffles): on return lane l holds the total of element l in v[0].

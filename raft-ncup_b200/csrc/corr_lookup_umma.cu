@@ -237,14 +237,9 @@ __device__ __forceinline__ void lookup_epilogue(const EpiCtx& c, int& ch, int l)
 #endif
     const size_t base = (static_cast<size_t>(c.b) * HW + qy * p.W + qx) * p.ldo + l * kLvlStride;
     auto emit = [&](const float (&v)[8], int gq) {
-      __half2 hh[4], ll[4];
+      uint32_t hh[4], ll[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float v0 = fminf(fmaxf(v[2 * j], -65504.f), 65504.f), v1 = fminf(fmaxf(v[2 * j + 1], -65504.f), 65504.f);
-        hh[j] = __floats2half2_rn(v0, v1);
-        const float2 back = __half22float2(hh[j]);
-        ll[j] = __floats2half2_rn(v0 - back.x, v1 - back.y);
-      }
+      for (int j = 0; j < 4; ++j) split_pair(v[2 * j], v[2 * j + 1], hh[j], ll[j]);
       *reinterpret_cast<uint4*>(p.out_hi + base + gq * 8) = *reinterpret_cast<uint4*>(hh);
       *reinterpret_cast<uint4*>(p.out_lo + base + gq * 8) = *reinterpret_cast<uint4*>(ll);
     };

@@ -1,5 +1,6 @@
 // Shared helpers for the rnc kernels (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -64,6 +65,19 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// Exact hi/lo split of a pair of floats into halves: hi = rn(v) saturated to +-65504 (one F2FP.SATFINITE), lo = rn(v - hi).
+// |v| <= 65504: hi + lo reproduces v to 22 significant bits.  Beyond the half range both parts saturate (finite, never inf).
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+__device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  hi = pack_half2_sat(v0, v1);
+  const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = pack_half2_sat(v0 - back.x, v1 - back.y);
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
