@@ -33,7 +33,7 @@ typedef enum {
 } rnc_status;
 
 /* Library identity / diagnostics. */
-int rnc_abi_version(void);                 /* bumps on any signature change (now 6) */
+int rnc_abi_version(void);                 /* bumps on any signature change (now 7) */
 const char* rnc_build_info(void);          /* e.g. "sm_100a nvcc 12.9" */
 const char* rnc_status_string(int status);
 int rnc_last_cuda_error(void);             /* cudaError_t of the last failed launch on this thread */
@@ -165,6 +165,8 @@ typedef struct {
   int flags;                           /* RNC_CONV_*                                                                 */
   double* stats;                       /* optional (RNC_EPI_LINEAR + out_f32 only): [B][cout][2] sum / sum of squares of the
                                         * outputs, ACCUMULATED (caller keeps it zeroed: rnc_instnorm_finalize re-zeroes) */
+  const float* add; int ldadd;         /* optional: fp32 [B*H*W][ldadd] added to the pre-activation (after bias), e.g. the
+                                        * hoisted contribution of input channels that do not change between calls */
 } rnc_conv_umma_desc;
 
 int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream);

@@ -42,6 +42,7 @@ struct Params {
   float* h; int ldh;
   float* aux0; int ldaux;
   const float* res; int ldres;
+  const float* add; int ldadd;        // optional fp32 addend of the pre-activation, [pixel][ldadd]
   double* stats;                      // [B][cout][2]: per-(image, channel) sum / sum of squares of the outputs, accumulated
 };
 
@@ -285,6 +286,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
           v[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]) + __uint_as_float(rc[4 * q + 1]), p.unscale, bv.y);
           v[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]) + __uint_as_float(rc[4 * q + 2]), p.unscale, bv.z);
           v[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]) + __uint_as_float(rc[4 * q + 3]), p.unscale, bv.w);
+        }
+        if (p.add != nullptr && valid) {
+          // hoisted part of the layer (input channels that are constant across calls), computed once by another launch
+          const float4* ap = reinterpret_cast<const float4*>(p.add + pix * p.ldadd + n);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 a = __ldg(ap + q);
+            v[4 * q] += a.x; v[4 * q + 1] += a.y; v[4 * q + 2] += a.z; v[4 * q + 3] += a.w;
+          }
         }
         if (use_stats) {
           // InstanceNorm statistics of this layer's output (extractor.py:128-129), fused here instead of a pass over the
@@ -539,6 +549,7 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   if (d.epilogue == RNC_EPI_RELU_FLOW && (d.coutpad < d.cout + 2 || !d.aux0 || !d.out_hi)) return RNC_ERR_BAD_SHAPE;
   if (d.out_hi && (!d.out_lo || (d.ldo_split & 7) || !aligned16(d.out_hi) || !aligned16(d.out_lo))) return RNC_ERR_BAD_POINTER;
   if (d.out_f32 && ((d.ldo_f32 & 3) || !aligned16(d.out_f32))) return RNC_ERR_BAD_POINTER;
+  if (d.add && ((d.ldadd & 3) || d.ldadd < d.coutpad || !aligned16(d.add))) return RNC_ERR_BAD_POINTER;
   if (d.stats && (d.epilogue != RNC_EPI_LINEAR || !d.out_f32 || d.coutpad > 128)) return RNC_ERR_UNSUPPORTED;
   switch (d.epilogue) {
     case RNC_EPI_RELU_ADD_RELU:
@@ -601,6 +612,7 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   p.out_hi = static_cast<__half*>(d.out_hi); p.out_lo = static_cast<__half*>(d.out_lo); p.ldo_split = d.ldo_split;
   p.h = d.h; p.ldh = d.ldh; p.aux0 = d.aux0; p.ldaux = d.ldaux; p.res = d.res; p.ldres = d.ldres;
   p.stats = d.stats;
+  p.add = d.add; p.ldadd = d.ldadd;
 
   CUtensorMap maps[6];
   bool ok = make_in_map(&maps[0], d.in0_hi, d.c0, d.ld0, d.B, Hin, Win, box_w, box_h, stride) &&

@@ -177,6 +177,7 @@ class EncoderRunner:
                   out_f32=ws.f2_pyr.data_ptr(), ldo_f32=256)
         # ---- cnet on frame 1
         self._trunk(pc, bufs, image1.contiguous(), B, Hin, Win)
+        ws.gru_const_valid = False                              # inp changes: the GRU's hoisted share must be recomputed
         eng.uconv(B, h8, w8, bufs.XS[2].ptrs(), 128, 128, pc.head, E.EPI_TANH_RELU, out_f32=ws.h.data_ptr(), ldo_f32=128,
                   out_split=ws.hx.ptrs(), ldo_split=HX_LD)
         return h8, w8

@@ -76,10 +76,18 @@ class PackedUpdateUmma:
         self.convf1_mm = UmmaWeights(wf.permute(0, 2, 3, 1).reshape(wf.shape[0], 98, 1, 1), e.convf1.bias, [98])
         self.convf2 = UmmaWeights(e.convf2.weight, e.convf2.bias, [128])
         self.conv = UmmaWeights(e.conv.weight, e.conv.bias, [256], extra_cout=2)
-        self.zr1 = UmmaWeights(cat([g.convz1.weight, g.convr1.weight], 0), cat([g.convz1.bias, g.convr1.bias], 0), [HX_LD])
-        self.q1 = UmmaWeights(g.convq1.weight, g.convq1.bias, [128, 256])
-        self.zr2 = UmmaWeights(cat([g.convz2.weight, g.convr2.weight], 0), cat([g.convz2.bias, g.convr2.bias], 0), [HX_LD])
-        self.q2 = UmmaWeights(g.convq2.weight, g.convq2.bias, [128, 256])
+        # SepConvGRU (update.py:33-60).  Its input cat([h, inp, motion]) holds 128 channels (`inp`, the context features) that do
+        # not change over the iterations: their share of every gate pre-activation is computed once per forward (`*_c`,
+        # biases included) and added in the per-iteration layers' epilogues, which then run over K = 256*5 instead of 384*5.
+        def gate(convs):
+            wt = cat([c.weight for c in convs], 0).detach().float()          # [Cout, 384 = h | inp | motion, kh, kw]
+            bs = cat([c.bias for c in convs], 0)
+            it = UmmaWeights(cat([wt[:, :128], wt[:, 256:]], 1), None, [128, 128])
+            return it, UmmaWeights(wt[:, 128:256], bs, [128])
+        self.zr1, self.zr1_c = gate([g.convz1, g.convr1])
+        self.q1, self.q1_c = gate([g.convq1])
+        self.zr2, self.zr2_c = gate([g.convz2, g.convr2])
+        self.q2, self.q2_c = gate([g.convq2])
         self.fh1 = UmmaWeights(fh.conv1.weight, fh.conv1.bias, [128])
         # FlowHead.conv2 (3x3, 256 -> 2): as a 1x1 layer with one output pair per tap (18 -> 32 columns, K = 256 instead of
         # 2304), summed over the shifted neighbours by rnc_flow_tap_gather_fwd
@@ -135,6 +143,10 @@ class UmmaWorkspace:
         self.rh = SplitBuf(M, 128, device)
         self.h = torch.zeros(M, 128, **f)            # fp32 master copy of the GRU state
         self.z = torch.empty(M, 128, **f)
+        # hoisted context-feature share of the GRU gate pre-activations (valid until inp changes)
+        self.czr1, self.czr2 = torch.empty(M, 256, **f), torch.empty(M, 256, **f)
+        self.cq1, self.cq2 = torch.empty(M, 128, **f), torch.empty(M, 128, **f)
+        self.gru_const_valid = False
         self.fh = SplitBuf(M, 256, device)
         self.fh2p = torch.empty(M, 32, **f)      # FlowHead.conv2 per-tap partial sums
         self.tmp = torch.empty(M, 256, **f)
@@ -199,11 +211,12 @@ class UmmaEngine(Engine):
 
     # ------------------------------------------------------------------ one tensor-core convolution
     def uconv(self, B, H, W, in0, c0, ld0, wt, epi, out_f32=0, ldo_f32=0, out_split=(0, 0), ldo_split=0, in1=(0, 0), c1=0, ld1=0,
-              h=0, ldh=0, aux0=0, ldaux=0, stride=1, hin=0, win=0, res=0, ldres=0, flags=None, stats=0):
+              h=0, ldh=0, aux0=0, ldaux=0, stride=1, hin=0, win=0, res=0, ldres=0, flags=None, stats=0, add=0, ldadd=0):
         """One rnc_conv2d_umma_fwd call.  H, W are the OUTPUT dims; for stride 2 pass the input dims as hin, win."""
         d = UmmaConvDesc()
         d.stride, d.hin, d.win, d.res, d.ldres = stride, hin, win, res, ldres
         d.stats = stats
+        d.add, d.ldadd = add, ldadd
         d.flags = self.conv_flags if flags is None else flags
         d.in0_hi, d.in0_lo, d.c0, d.ld0 = in0[0], in0[1], c0, ld0
         d.in1_hi, d.in1_lo, d.c1, d.ld1 = in1[0], in1[1], c1, ld1
@@ -308,11 +321,18 @@ class UmmaEngine(Engine):
                    aux0=ws.coords1.data_ptr())
         # SepConvGRU (update.py:45-60)
         hp = ws.h.data_ptr()
-        for zr, q in ((pk.zr1, pk.q1), (pk.zr2, pk.q2)):
-            self.uconv(B, H, W, ws.hx.ptrs(), HX_LD, HX_LD, zr, E.EPI_GRU_ZR, out_split=ws.rh.ptrs(), ldo_split=128,
-                       h=hp, ldh=128, aux0=ws.z.data_ptr(), ldaux=128)
-            self.uconv(B, H, W, ws.rh.ptrs(), 128, 128, q, E.EPI_GRU_Q, in1=ws.hx.ptrs(128), c1=256, ld1=HX_LD,
-                       out_split=ws.hx.ptrs(), ldo_split=HX_LD, h=hp, ldh=128, aux0=ws.z.data_ptr(), ldaux=128)
+        if not ws.gru_const_valid:
+            # the context channels' share of the gate pre-activations (+ biases): once per forward
+            for wt, buf in ((pk.zr1_c, ws.czr1), (pk.q1_c, ws.cq1), (pk.zr2_c, ws.czr2), (pk.q2_c, ws.cq2)):
+                self.uconv(B, H, W, ws.hx.ptrs(128), 128, HX_LD, wt, E.EPI_LINEAR, out_f32=buf.data_ptr(), ldo_f32=wt.coutpad)
+            ws.gru_const_valid = True
+        for zr, q, czr, cq in ((pk.zr1, pk.q1, ws.czr1, ws.cq1), (pk.zr2, pk.q2, ws.czr2, ws.cq2)):
+            self.uconv(B, H, W, ws.hx.ptrs(), 128, HX_LD, zr, E.EPI_GRU_ZR, in1=ws.hx.ptrs(256), c1=128, ld1=HX_LD,
+                       out_split=ws.rh.ptrs(), ldo_split=128, h=hp, ldh=128, aux0=ws.z.data_ptr(), ldaux=128,
+                       add=czr.data_ptr(), ldadd=256)
+            self.uconv(B, H, W, ws.rh.ptrs(), 128, 128, q, E.EPI_GRU_Q, in1=ws.hx.ptrs(256), c1=128, ld1=HX_LD,
+                       out_split=ws.hx.ptrs(), ldo_split=HX_LD, h=hp, ldh=128, aux0=ws.z.data_ptr(), ldaux=128,
+                       add=cq.data_ptr(), ldadd=128)
         # FlowHead (update.py:13-14) + coords1 += delta (raft_nc_dbl.py:157)
         self.uconv(B, H, W, ws.hx.ptrs(), 128, HX_LD, pk.fh1, E.EPI_RELU, out_split=ws.fh.ptrs(), ldo_split=256)
         self.uconv(B, H, W, ws.fh.ptrs(), 256, 256, pk.fh2, E.EPI_LINEAR, out_f32=ws.fh2p.data_ptr(), ldo_f32=32)
@@ -323,6 +343,7 @@ class UmmaEngine(Engine):
             self.uconv(B, H, W, ws.mh.ptrs(), 256, 256, pk.m2, E.EPI_LINEAR, out_f32=ws.mask.data_ptr(), ldo_f32=576)
 
     def load_state(self, ws, net, inp):
+        ws.gru_const_valid = False
         B, _, H, W = net.shape
         s = _stream()
         M = B * H * W

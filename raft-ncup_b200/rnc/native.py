@@ -10,7 +10,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librnc.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 (EPI_LINEAR, EPI_RELU, EPI_SIGMOID, EPI_GRU_ZR, EPI_GRU_Q, EPI_RELU_FLOW, EPI_RELU_ADD_RELU, EPI_TANH_RELU,
  EPI_FLOW_DELTA) = range(9)
@@ -52,7 +52,7 @@ class UmmaConvDesc(C.Structure):
                 ("B", _i), ("H", _i), ("W", _i),
                 ("cout", _i), ("kh", _i), ("kw", _i), ("epilogue", _i),
                 ("stride", _i), ("hin", _i), ("win", _i),
-                ("res", _vp), ("ldres", _i), ("flags", _i), ("stats", _vp)]
+                ("res", _vp), ("ldres", _i), ("flags", _i), ("stats", _vp), ("add", _vp), ("ldadd", _i)]
 
 
 # name -> (restype, argtypes); every symbol include/rnc.h declares
