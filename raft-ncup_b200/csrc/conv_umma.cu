@@ -23,7 +23,7 @@ namespace umma {
 constexpr int kThreads = 320;        // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue (2 per lane group)
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kMaxSA = 4, kMaxSB = 8;
+constexpr int kMaxSA = 4, kMaxSB = 12;
 enum { MODE_TAP = 0, MODE_ROWHALO = 1, MODE_COLHALO = 2 };
 
 struct Params {
@@ -33,6 +33,7 @@ struct Params {
   int nblk0, nblk;                    // 64-channel blocks in segment 0 / total
   int a_plane, SA, SB;                // bytes per A half-plane stage (rows*128, 1024-aligned), ring depths
   int use_base_offset;
+  int resident_b;                     // the layer's whole weight matrix fits the B ring: loaded once per CTA, never released
   int probe_nob;                      // developer probe (RNC_CONV_PROBE_NOB=1): skip the weight loads after the first ring fill
   int cout, epilogue;
   float unscale;
@@ -156,6 +157,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
               const int tap = p.mode == MODE_TAP ? g : p.mode == MODE_ROWHALO ? g * p.kw + t : t;
               const int sb = b_it % p.SB, pb = (b_it / p.SB) & 1;
               ++b_it;
+              if (p.resident_b && item != static_cast<int>(blockIdx.x)) continue;     // weights already resident
               mbar_wait(&b_empty[sb], pb ^ 1);
               const int kcol = (tap * p.nblk + cb) * kBK;
               if (elect_one()) {
@@ -195,7 +197,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
             for (int t = 0; t < T; ++t) {
               const int sb = b_it % p.SB, pb = (b_it / p.SB) & 1;
               ++b_it;
-              mbar_wait(&b_full[sb], pb);
+              mbar_wait(&b_full[sb], p.resident_b ? 0 : pb);
               tcgen05_fence_after();
               const uint32_t ar = a_base + sa * a_stage + t * shift_rows * 128;
               const uint64_t ah = p.use_base_offset ? smem_desc_sw128_shift(ar) : smem_desc_sw128(ar);
@@ -220,7 +222,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
                     umma_f16(d_corr, al + 2 * k, bh + 2 * k, idesc, 1);
                   }
                 }
-                umma_commit(&b_empty[sb]);
+                if (!p.resident_b) umma_commit(&b_empty[sb]);
               }
               __syncwarp();
               acc = 1;
@@ -472,9 +474,20 @@ static int launch(const CUtensorMap* maps, Params& p, cudaStream_t stream, int m
   p.SA = 2;
   while (p.SA < kMaxSA && budget - (p.SA + 1) * a_stage >= 3 * b_stage) ++p.SA;
   int sb = (budget - p.SA * a_stage) / b_stage;
-  p.SB = sb > kMaxSB ? kMaxSB : sb < 2 ? 2 : sb;
+  p.SB = sb > 8 ? 8 : sb < 2 ? 2 : sb;
   if (max_sa > 0 && p.SA > max_sa) p.SA = max_sa;      // debug knobs (rnc_conv_umma_desc.flags bits 8-15)
   if (max_sb > 0 && p.SB > max_sb) p.SB = max_sb;
+  // Small layers (64 -> 64 3x3: 9 stages of 16 KB): keep the whole weight matrix in the ring for the CTA's lifetime instead
+  // of re-streaming it for every pixel tile (the shared-memory fill bandwidth is what bounds narrow tiles).
+  p.resident_b = 0;
+  {
+    const int nb = p.kh * p.kw * p.nblk;
+    const int hard = 227 * 1024 - 1024 - 512 - 8192 - 1024;
+    if (p.ntn == 1 && nb <= kMaxSB && nb > p.SB && max_sb == 0 && 2 * a_stage + nb * b_stage <= hard) {
+      p.resident_b = 1; p.SB = nb; p.SA = (hard - nb * b_stage) / a_stage;
+      if (p.SA > kMaxSA) p.SA = kMaxSA;
+    }
+  }
   const int smem = p.SA * a_stage + p.SB * 2 * C::kBTile + 1024 + 512 + (BN <= 128 ? 8192 : 0);   // + fp64 statistics slots
   static unsigned long long done = 0;
   if (int st = ensure_dyn_smem(conv_umma_kernel<BN>, 227 * 1024, &done)) return st;
