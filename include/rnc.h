@@ -119,6 +119,7 @@ typedef enum {
 /* rnc_conv_umma_desc.flags */
 #define RNC_CONV_NO_HALO 1          /* force one A tile per filter tap (disable the row/column halo sharing) */
 #define RNC_CONV_BASE_OFFSET 2      /* debug: set the descriptor base_offset for row-shifted taps (wrong on B200) */
+#define RNC_CONV_NO_PAIR 8          /* never use the CTA-pair (cta_group::2) form for this call */
 #define RNC_CONV_SPLIT_N 4          /* 256-column layers as two 128-column items per pixel tile (double-buffered TMEM) */
 
 typedef struct {

@@ -85,7 +85,10 @@ struct Cfg {
   static constexpr int kTmemCols = BN <= 32 ? 128 : BN <= 64 ? 256 : 512;
 };
 
-template <int BN>
+// PAIR: two CTAs of a cluster (adjacent pixel tiles, same weights) run each MMA together (cta_group::2, M = 256): every CTA
+// stages its own A tile and HALF of the weight tile, so the shared-memory fill and operand-read traffic per SM drop by the
+// weight share — the resource that bounds the single-CTA form.  The leader (rank 0) issues all MMAs.
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__ CUtensorMap mA0l,
                  const __grid_constant__ CUtensorMap mA1h, const __grid_constant__ CUtensorMap mA1l,
@@ -96,7 +99,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
   const int a_stage = 2 * p.a_plane;
   unsigned char* sA = smem;
   unsigned char* sB = smem + p.SA * a_stage;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.SB * 2 * C::kBTile);
+  constexpr int kBStageBytes = PAIR ? C::kBTile : 2 * C::kBTile;      // [hi | lo] (half-)planes of one K block
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.SB * kBStageBytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kMaxSA;
   uint64_t* b_full = a_empty + kMaxSA;
@@ -108,20 +112,28 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
 
   pdl_trigger();                       // the next kernel in the stream may begin its prologue on SMs this grid has left
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int items = p.ntiles * p.ntn;
   const int tpi = p.tiles_x * p.tiles_y;
   const int G = p.mode == MODE_TAP ? p.kh * p.kw : p.mode == MODE_ROWHALO ? p.kh : 1;     // A-stage groups per channel block
   const int T = p.mode == MODE_TAP ? 1 : p.mode == MODE_ROWHALO ? p.kw : p.kh;            // taps sharing one A stage
+  // work items: (pixel tile [pair], column tile); a pair's two CTAs take adjacent pixel tiles of the same item
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int ptiles = PAIR ? (p.ntiles + 1) / 2 : p.ntiles;
+  const int items = ptiles * p.ntn;
+  const int item0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int item_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  constexpr int kBHalf = PAIR ? C::kBTile / 2 : C::kBTile;          // bytes of one weight half-plane staged by this CTA
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], PAIR ? 16 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  if (warp == 1) { if (PAIR) tmem_alloc_pair(tmem_slot, C::kTmemCols); else tmem_alloc(tmem_slot, C::kTmemCols); }
   tcgen05_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();        // the peer's barriers exist before anything signals them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                          // everything above overlapped the predecessor's tail; its results are visible from here
@@ -131,9 +143,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
     // The whole warp runs the loop so that addresses / coordinates stay in uniform registers (UTMALDG and UTCHMMA take
     // uniform operands; a loop under `if (lane == 0)` forces an R2UR chain in front of every issue); one elected lane issues.
     {
+      // pair: both CTAs' loads complete on the LEADER's full barriers (it alone waits for operands); each CTA recycles its
+      // own stages when the leader's MMA completion reaches its own empty barriers
+      const uint32_t a_full_l = PAIR ? mapa_u32(smem_u32(a_full), 0) : 0u, b_full_l = PAIR ? mapa_u32(smem_u32(b_full), 0) : 0u;
       int a_it = 0, b_it = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int tile = item / p.ntn, n0 = (item - tile * p.ntn) * BN;
+      for (int item = item0; item < items; item += item_step) {
+        const int ptile = item / p.ntn, n0 = (item - ptile * p.ntn) * BN;
+        const int tile = PAIR ? ptile * 2 + static_cast<int>(rank) : ptile;     // a ghost tile (odd count) loads zero-filled boxes
         const int b = tile / tpi, tr = tile - b * tpi;
         const int y0 = (tr / p.tiles_x) * p.TH, x0 = (tr % p.tiles_x) * p.TW;
         for (int g = 0; g < G; ++g) {
@@ -148,20 +164,31 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
             const bool seg0 = cb < p.nblk0;
             const int c = (seg0 ? cb : cb - p.nblk0) * kBK;
             if (elect_one()) {
-              mbar_expect_tx(&a_full[sa], a_stage);
-              tma_load_4d(sA + sa * a_stage, seg0 ? &mA0h : &mA1h, &a_full[sa], c, cx, cy, b);
-              tma_load_4d(sA + sa * a_stage + p.a_plane, seg0 ? &mA0l : &mA1l, &a_full[sa], c, cx, cy, b);
+              if (PAIR) {
+                if (leader) mbar_expect_tx(&a_full[sa], 2 * a_stage);
+                tma_load_4d_pair(sA + sa * a_stage, seg0 ? &mA0h : &mA1h, a_full_l + sa * 8, c, cx, cy, b);
+                tma_load_4d_pair(sA + sa * a_stage + p.a_plane, seg0 ? &mA0l : &mA1l, a_full_l + sa * 8, c, cx, cy, b);
+              } else {
+                mbar_expect_tx(&a_full[sa], a_stage);
+                tma_load_4d(sA + sa * a_stage, seg0 ? &mA0h : &mA1h, &a_full[sa], c, cx, cy, b);
+                tma_load_4d(sA + sa * a_stage + p.a_plane, seg0 ? &mA0l : &mA1l, &a_full[sa], c, cx, cy, b);
+              }
             }
             __syncwarp();
             for (int t = 0; t < T; ++t) {
               const int tap = p.mode == MODE_TAP ? g : p.mode == MODE_ROWHALO ? g * p.kw + t : t;
               const int sb = b_it % p.SB, pb = (b_it / p.SB) & 1;
               ++b_it;
-              if (p.resident_b && item != static_cast<int>(blockIdx.x)) continue;     // weights already resident
+              if (p.resident_b && item != item0) continue;     // weights already resident
               mbar_wait(&b_empty[sb], pb ^ 1);
               const int kcol = (tap * p.nblk + cb) * kBK;
               if (elect_one()) {
-                if (p.probe_nob && b_it > p.SB) {
+                if (PAIR) {                  // this CTA's half of the weight rows, hi and lo planes
+                  const int nrow = n0 + static_cast<int>(rank) * (BN / 2);
+                  if (leader) mbar_expect_tx(&b_full[sb], 2 * kBStageBytes);
+                  tma_load_2d_pair(sB + sb * kBStageBytes, &mBh, b_full_l + sb * 8, kcol, nrow);
+                  tma_load_2d_pair(sB + sb * kBStageBytes + kBHalf, &mBl, b_full_l + sb * 8, kcol, nrow);
+                } else if (p.probe_nob && b_it > p.SB) {
                   mbar_arrive(&b_full[sb]);
                 } else {
                   mbar_expect_tx(&b_full[sb], 2 * C::kBTile);
@@ -177,13 +204,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
-    {
-      const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(kBM >> 4) << 24);
+    if (leader) {
+      const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>((PAIR ? 2 * kBM : kBM) >> 4) << 24);
       const uint32_t idesc2 = (1u << 4) | (static_cast<uint32_t>((2 * BN <= 256 ? 2 * BN : BN) >> 3) << 17) | (static_cast<uint32_t>(kBM >> 4) << 24);
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
       const int shift_rows = p.mode == MODE_ROWHALO ? 1 : p.mode == MODE_COLHALO ? p.TW : 0;
       int a_it = 0, b_it = 0, t_it = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x, ++t_it) {
+      for (int item = item0; item < items; item += item_step, ++t_it) {
         const int buf = t_it % C::kBufs, use = t_it / C::kBufs;
         mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
         tcgen05_fence_after();
@@ -202,35 +229,46 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
               const uint32_t ar = a_base + sa * a_stage + t * shift_rows * 128;
               const uint64_t ah = p.use_base_offset ? smem_desc_sw128_shift(ar) : smem_desc_sw128(ar);
               const uint64_t al = p.use_base_offset ? smem_desc_sw128_shift(ar + p.a_plane) : smem_desc_sw128(ar + p.a_plane);
-              const uint32_t br = b_base + sb * 2 * C::kBTile;
-              const uint64_t bh = smem_desc_sw128(br), bl = smem_desc_sw128(br + C::kBTile);
+              const uint32_t br = b_base + sb * kBStageBytes;
+              const uint64_t bh = smem_desc_sw128(br), bl = smem_desc_sw128(br + kBHalf);
               if (elect_one()) {
-                if (BN <= 128) {
-                  // The hi and lo weight planes are adjacent in the stage and `main`, `corr` adjacent in TMEM, so
-                  // x_hi * [w_hi | w_lo] is ONE instruction of 2*BN columns: x_hi is fetched from shared memory once
-                  // instead of twice (a 128-column instruction needs the full 128 B/clk of shared-memory bandwidth).
+                if (PAIR) {
+                  // M = 256 across the pair: each CTA's tensor core reads its own A rows and both CTAs' weight halves
 #pragma unroll
                   for (int k = 0; k < kBK / 16; ++k) {
-                    umma_f16(d_main, ah + 2 * k, bh + 2 * k, idesc2, k == 0 ? acc : 1u);
-                    umma_f16(d_corr, al + 2 * k, bh + 2 * k, idesc, 1);
+                    umma_f16_pair(d_main, ah + 2 * k, bh + 2 * k, idesc, k == 0 ? acc : 1u);
+                    umma_f16_pair(d_corr, ah + 2 * k, bl + 2 * k, idesc, k == 0 ? acc : 1u);
+                    umma_f16_pair(d_corr, al + 2 * k, bh + 2 * k, idesc, 1);
                   }
+                  if (!p.resident_b) umma_commit_pair(&b_empty[sb]);
                 } else {
+                  if (BN <= 128) {
+                    // The hi and lo weight planes are adjacent in the stage and `main`, `corr` adjacent in TMEM, so
+                    // x_hi * [w_hi | w_lo] is ONE instruction of 2*BN columns: x_hi is fetched from shared memory once
+                    // instead of twice (a 128-column instruction needs the full 128 B/clk of shared-memory bandwidth).
 #pragma unroll
-                  for (int k = 0; k < kBK / 16; ++k) {
-                    umma_f16(d_main, ah + 2 * k, bh + 2 * k, idesc, k == 0 ? acc : 1u);
-                    umma_f16(d_corr, ah + 2 * k, bl + 2 * k, idesc, k == 0 ? acc : 1u);
-                    umma_f16(d_corr, al + 2 * k, bh + 2 * k, idesc, 1);
+                    for (int k = 0; k < kBK / 16; ++k) {
+                      umma_f16(d_main, ah + 2 * k, bh + 2 * k, idesc2, k == 0 ? acc : 1u);
+                      umma_f16(d_corr, al + 2 * k, bh + 2 * k, idesc, 1);
+                    }
+                  } else {
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) {
+                      umma_f16(d_main, ah + 2 * k, bh + 2 * k, idesc, k == 0 ? acc : 1u);
+                      umma_f16(d_corr, ah + 2 * k, bl + 2 * k, idesc, k == 0 ? acc : 1u);
+                      umma_f16(d_corr, al + 2 * k, bh + 2 * k, idesc, 1);
+                    }
                   }
+                  if (!p.resident_b) umma_commit(&b_empty[sb]);
                 }
-                if (!p.resident_b) umma_commit(&b_empty[sb]);
               }
               __syncwarp();
               acc = 1;
             }
-            if (elect_one()) umma_commit(&a_empty[sa]);
+            if (elect_one()) { if (PAIR) umma_commit_pair(&a_empty[sa]); else umma_commit(&a_empty[sa]); }
             __syncwarp();
           }
-        if (elect_one()) umma_commit(&acc_full[buf]);
+        if (elect_one()) { if (PAIR) umma_commit_pair(&acc_full[buf]); else umma_commit(&acc_full[buf]); }
         __syncwarp();
       }
     }
@@ -259,13 +297,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
     if (use_stats) {
       for (int ci = 0; ci < kHalfN; ++ci) { my_acc[ci * 64] = 0.0; my_acc[ci * 64 + 1] = 0.0; }
     }
+    const uint32_t acc_empty_l = PAIR ? mapa_u32(smem_u32(acc_empty), 0) : 0u;     // the leader's MMA warp waits for both CTAs
     int t_it = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x, ++t_it) {
-      const int tile = item / p.ntn, n0 = (item - tile * p.ntn) * BN;
+    for (int item = item0; item < items; item += item_step, ++t_it) {
+      const int ptile = item / p.ntn, n0 = (item - ptile * p.ntn) * BN;
+      const int tile = PAIR ? ptile * 2 + static_cast<int>(rank) : ptile;
       const int b = tile / tpi, tr = tile - b * tpi;
-      if (use_stats && (b != acc_b || n0 != acc_n0)) { flush_stats(); acc_b = b; acc_n0 = n0; }
+      const bool ghost = tile >= p.ntiles;                     // odd tile count: the pair's second CTA idles through this item
+      if (use_stats && !ghost && (b != acc_b || n0 != acc_n0)) { flush_stats(); acc_b = b; acc_n0 = n0; }
       const int y = (tr / p.tiles_x) * p.TH + ml / p.TW, x = (tr % p.tiles_x) * p.TW + ml % p.TW;
-      const bool valid = y < p.H && x < p.W;
+      const bool valid = !ghost && y < p.H && x < p.W;
       const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
       const int buf = t_it % C::kBufs, use = t_it / C::kBufs;
       mbar_wait(&acc_full[buf], use & 1);
@@ -417,7 +458,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
       // this warp has finished reading the accumulator buffer (tcgen05.wait::ld inside tmem_ld32)
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (lane == 0) { if (PAIR) mbar_arrive_cluster(acc_empty_l + buf * 8); else mbar_arrive(&acc_empty[buf]); }
     }
     if (use_stats) flush_stats();
   }
@@ -425,9 +466,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
   // ------------------------------------------------------------------ teardown
   tcgen05_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();        // the peer may still be multicasting to this CTA's barriers / reading its weight half
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, C::kTmemCols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, C::kTmemCols); else tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
@@ -464,13 +506,12 @@ static int sm_count() {
   return n;
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 static int launch(const CUtensorMap* maps, Params& p, cudaStream_t stream, int max_sa, int max_sb) {
   using C = Cfg<BN>;
-  // ring depths: A double buffered, B as deep as fits ~200 KB
   const int a_stage = 2 * p.a_plane;
   // ring depths within ~208 KB: both rings hide the same TMA latency, so deepen A (up to 4) while B keeps >= 3 stages
-  const int budget = 208 * 1024, b_stage = 2 * C::kBTile;
+  const int budget = 208 * 1024, b_stage = PAIR ? C::kBTile : 2 * C::kBTile;      // a pair's CTA stages half of the weight rows
   p.SA = 2;
   while (p.SA < kMaxSA && budget - (p.SA + 1) * a_stage >= 3 * b_stage) ++p.SA;
   int sb = (budget - p.SA * a_stage) / b_stage;
@@ -488,15 +529,36 @@ static int launch(const CUtensorMap* maps, Params& p, cudaStream_t stream, int m
       if (p.SA > kMaxSA) p.SA = kMaxSA;
     }
   }
-  const int smem = p.SA * a_stage + p.SB * 2 * C::kBTile + 1024 + 512 + (BN <= 128 ? 8192 : 0);   // + fp64 statistics slots
+  const int smem = p.SA * a_stage + p.SB * b_stage + 1024 + 512 + (BN <= 128 ? 8192 : 0);   // + fp64 statistics slots
   static unsigned long long done = 0;
-  if (int st = ensure_dyn_smem(conv_umma_kernel<BN>, 227 * 1024, &done)) return st;
-  const int items = p.ntiles * p.ntn;
-  const int grid = items < sm_count() ? items : sm_count();
-  cudaError_t e = launch_pdl(conv_umma_kernel<BN>, dim3(grid), dim3(kThreads), smem, stream, maps[0], maps[1], maps[2], maps[3], maps[4],
-                             maps[5], p);
+  if (int st = ensure_dyn_smem(conv_umma_kernel<BN, PAIR>, 227 * 1024, &done)) return st;
+  const int items = (PAIR ? (p.ntiles + 1) / 2 : p.ntiles) * p.ntn;
+  const int slots = PAIR ? sm_count() / 2 : sm_count();
+  const int grid = (items < slots ? items : slots) * (PAIR ? 2 : 1);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (PAIR) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, PAIR>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   if (e != cudaSuccess) { g_last_cuda_error = static_cast<int>(e); return RNC_ERR_CUDA; }
   return after_launch();
+}
+
+// RNC_CONV_PAIR=1: CTA-pair (cta_group::2) form of the convolution
+static bool pair_enabled() {
+  static const int on = [] { const char* e = getenv("RNC_CONV_PAIR"); return (e && e[0] == '1') ? 1 : 0; }();
+  return on != 0;
 }
 
 }  // namespace umma
@@ -636,15 +698,26 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   } else {
     maps[2] = maps[0]; maps[3] = maps[1];
   }
-  ok = ok && make_w_map(&maps[4], d.w_hi, d.ktot, d.coutpad, bn) && make_w_map(&maps[5], d.w_lo, d.ktot, d.coutpad, bn);
+  const bool pair = umma::pair_enabled() && (d.flags & RNC_CONV_NO_PAIR) == 0;
+  ok = ok && make_w_map(&maps[4], d.w_hi, d.ktot, d.coutpad, pair ? bn / 2 : bn) && make_w_map(&maps[5], d.w_lo, d.ktot, d.coutpad, pair ? bn / 2 : bn);
   if (!ok) return RNC_ERR_BAD_SHAPE;
 
   cudaStream_t s = as_stream(stream);
+  const int msa = (d.flags >> 8) & 15, msb = (d.flags >> 12) & 15;
+  if (pair) {
+    switch (bn) {
+      case 32: return launch<32, true>(maps, p, s, msa, msb);
+      case 64: return launch<64, true>(maps, p, s, msa, msb);
+      case 128: return launch<128, true>(maps, p, s, msa, msb);
+      case 192: return launch<192, true>(maps, p, s, msa, msb);
+      default: return launch<256, true>(maps, p, s, msa, msb);
+    }
+  }
   switch (bn) {
-    case 32: return launch<32>(maps, p, s, (d.flags >> 8) & 15, (d.flags >> 12) & 15);
-    case 64: return launch<64>(maps, p, s, (d.flags >> 8) & 15, (d.flags >> 12) & 15);
-    case 128: return launch<128>(maps, p, s, (d.flags >> 8) & 15, (d.flags >> 12) & 15);
-    case 192: return launch<192>(maps, p, s, (d.flags >> 8) & 15, (d.flags >> 12) & 15);
-    default: return launch<256>(maps, p, s, (d.flags >> 8) & 15, (d.flags >> 12) & 15);
+    case 32: return launch<32, false>(maps, p, s, msa, msb);
+    case 64: return launch<64, false>(maps, p, s, msa, msb);
+    case 128: return launch<128, false>(maps, p, s, msa, msb);
+    case 192: return launch<192, false>(maps, p, s, msa, msb);
+    default: return launch<256, false>(maps, p, s, msa, msb);
   }
 }
