@@ -555,9 +555,9 @@ static int launch(const CUtensorMap* maps, Params& p, cudaStream_t stream, int m
   return after_launch();
 }
 
-// RNC_CONV_PAIR=1: CTA-pair (cta_group::2) form of the convolution
+// CTA-pair (cta_group::2) form of the convolution: the default; RNC_CONV_PAIR=0 selects the single-CTA form
 static bool pair_enabled() {
-  static const int on = [] { const char* e = getenv("RNC_CONV_PAIR"); return (e && e[0] == '1') ? 1 : 0; }();
+  static const int on = [] { const char* e = getenv("RNC_CONV_PAIR"); return (e && e[0] == '0') ? 0 : 1; }();
   return on != 0;
 }
 
@@ -581,9 +581,15 @@ static int choose_bn(const rnc_conv_umma_desc& d, int bn_max, int stride) {
   else if (stride == 1 && (d.flags & RNC_CONV_NO_HALO) == 0 && d.kw == 1 && d.kh > 1 && d.W >= 16 && d.H >= 8) { TW = 16; TH = 8; }
   else { TW = 8; while (TW < d.W && TW < umma::kBM) TW <<= 1; TH = umma::kBM / TW; }
   const long ntiles = static_cast<long>(d.B) * ((d.W + TW - 1) / TW) * ((d.H + TH - 1) / TH);
-  const int sms = umma::sm_count();
+  // CTA-pair form (fitted to the same probe): the pair's leader waits for both CTAs' epilogues, so a single-buffered
+  // (> 128 columns) tile exposes ~12 K-steps per item, while narrow tiles no longer sit on the shared-memory bandwidth
+  const bool pair = umma::pair_enabled() && (d.flags & RNC_CONV_NO_PAIR) == 0;
   static const int cand[5] = {256, 192, 128, 64, 32};
-  static const float per_k[5] = {1.0f, 0.77f, 0.53f, 0.36f, 0.30f};
+  static const float per_k1[5] = {1.0f, 0.77f, 0.53f, 0.36f, 0.30f}, per_k2[5] = {1.0f, 0.8f, 0.6f, 0.40f, 0.34f};
+  const float* per_k = pair ? per_k2 : per_k1;
+  const float expose = pair ? 12.0f : 3.0f, per_item = pair ? 1.2f : 0.5f;
+  const long slots = pair ? umma::sm_count() / 2 : umma::sm_count();
+  const long ptiles = pair ? (ntiles + 1) / 2 : ntiles;
   int best = bn_max;
   float best_cost = 1e30f;
   for (int i = 0; i < 5; ++i) {
@@ -591,8 +597,8 @@ static int choose_bn(const rnc_conv_umma_desc& d, int bn_max, int stride) {
     if (bn > bn_max || d.coutpad % bn != 0) continue;
     if ((d.epilogue == RNC_EPI_TANH_RELU || d.epilogue == RNC_EPI_GRU_ZR) && bn < 64) continue;
     const int ntn = d.coutpad / bn;
-    const long rounds = (ntiles * ntn + sms - 1) / sms;
-    float item = ksteps * per_k[i] + 0.5f + (bn > 128 ? 3.0f * bn / 256.0f : 0.f);
+    const long rounds = (ptiles * ntn + slots - 1) / slots;
+    float item = ksteps * per_k[i] + per_item + (bn > 128 ? expose * bn / 256.0f : 0.f);
     if (ntn > 1) item *= 1.08f;
     const float cost = rounds * item;
     if (cost < best_cost * 0.97f) { best_cost = cost; best = bn; }     // wider wins near-ties
