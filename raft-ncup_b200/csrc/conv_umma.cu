@@ -358,7 +358,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
             float4* dst = reinterpret_cast<float4*>(p.aux0 + pix * p.ldaux + n);
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-              dst[q] = make_float4(sigmoidf_(v[4 * q]), sigmoidf_(v[4 * q + 1]), sigmoidf_(v[4 * q + 2]), sigmoidf_(v[4 * q + 3]));
+              dst[q] = make_float4(sigmoid_fast(v[4 * q]), sigmoid_fast(v[4 * q + 1]), sigmoid_fast(v[4 * q + 2]), sigmoid_fast(v[4 * q + 3]));
           } else {                 // r gate -> r*h as split halves
             const float4* hp = reinterpret_cast<const float4*>(p.h + pix * p.ldh + (n - Ch));
             float4 hreg[8];        // all loads first (h is read-only here): no load->store serialisation
@@ -367,8 +367,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const float4 hv = hreg[q];
-              v[4 * q + 0] = sigmoidf_(v[4 * q + 0]) * hv.x; v[4 * q + 1] = sigmoidf_(v[4 * q + 1]) * hv.y;
-              v[4 * q + 2] = sigmoidf_(v[4 * q + 2]) * hv.z; v[4 * q + 3] = sigmoidf_(v[4 * q + 3]) * hv.w;
+              v[4 * q + 0] = sigmoid_fast(v[4 * q + 0]) * hv.x; v[4 * q + 1] = sigmoid_fast(v[4 * q + 1]) * hv.y;
+              v[4 * q + 2] = sigmoid_fast(v[4 * q + 2]) * hv.z; v[4 * q + 3] = sigmoid_fast(v[4 * q + 3]) * hv.w;
             }
             uint4* dh = reinterpret_cast<uint4*>(p.out_hi + pix * p.ldo_split + (n - Ch));
             uint4* dl = reinterpret_cast<uint4*>(p.out_lo + pix * p.ldo_split + (n - Ch));
@@ -396,10 +396,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 z = zreg[q], hv = hreg[q];
-            v[4 * q + 0] = (1.f - z.x) * hv.x + z.x * tanhf(v[4 * q + 0]);
-            v[4 * q + 1] = (1.f - z.y) * hv.y + z.y * tanhf(v[4 * q + 1]);
-            v[4 * q + 2] = (1.f - z.z) * hv.z + z.z * tanhf(v[4 * q + 2]);
-            v[4 * q + 3] = (1.f - z.w) * hv.w + z.w * tanhf(v[4 * q + 3]);
+            v[4 * q + 0] = (1.f - z.x) * hv.x + z.x * tanh_fast(v[4 * q + 0]);
+            v[4 * q + 1] = (1.f - z.y) * hv.y + z.y * tanh_fast(v[4 * q + 1]);
+            v[4 * q + 2] = (1.f - z.z) * hv.z + z.z * tanh_fast(v[4 * q + 2]);
+            v[4 * q + 3] = (1.f - z.w) * hv.w + z.w * tanh_fast(v[4 * q + 3]);
             hp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
         } else if (epi == RNC_EPI_RELU || epi == RNC_EPI_RELU_FLOW) {
@@ -418,7 +418,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
           }
         } else if (epi == RNC_EPI_SIGMOID) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = sigmoidf_(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = sigmoid_fast(v[j]);
         } else if (epi == RNC_EPI_RELU_ADD_RELU) {
           // residual block tail (extractor.py:55): relu(x + relu(norm(conv(.)))) with the norm folded into the weights
           const float4* rp = reinterpret_cast<const float4*>(p.res + pix * p.ldres + n);
@@ -436,7 +436,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
           // context encoder head (raft_nc_dbl.py:138-140): first half tanh -> net, second half relu -> inp
           if (n < (p.cout >> 1)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = tanh_fast(v[j]);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);

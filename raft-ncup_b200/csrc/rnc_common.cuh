@@ -82,4 +82,22 @@ __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uin
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// Gate activations of the tensor-core epilogues: ex2.approx / rcp.approx based, a few instructions, branch-free, relative
+// error ~1e-6 (the libm forms cost 30-40 instructions each and the GRU epilogues are latency-bound on them).
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  return fast_rcp(1.0f + __expf(-x));                    // x << 0: exp -> inf, rcp -> 0; x >> 0: -> 1
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float ax = fabsf(x), x2 = x * x;
+  // |x| < 0.25: odd Taylor series through x^9 (truncation < 1e-8 relative); otherwise 1 - 2 / (exp(2|x|) + 1)
+  const float poly = x * (1.0f + x2 * (-0.33333334f + x2 * (0.13333334f + x2 * (-0.05396825f + x2 * 0.021869488f))));
+  const float big = 1.0f - 2.0f * fast_rcp(__expf(2.0f * fminf(ax, 20.0f)) + 1.0f);
+  return ax < 0.25f ? poly : copysignf(big, x);
+}
+
 }  // namespace rnc
