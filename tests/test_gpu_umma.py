@@ -140,6 +140,33 @@ def test_flow_head_conv2_as_taps_plus_gather(ueng):
     assert ueng.L.rnc_flow_tap_gather_fwd(vp(taps.data_ptr()), 16, vp(0), B, H, W, None, vp(coords.data_ptr()), None) != 0
 
 
+@pytest.mark.parametrize("cin,cout,kh,kw,B,H,W", [(128, 256, 3, 3, 3, 9, 128), (384, 128, 5, 1, 1, 17, 40), (64, 64, 3, 3, 2, 13, 150)])
+def test_umma_pair_and_single_cta_forms_agree(ueng, cin, cout, kh, kw, B, H, W):
+    """The CTA-pair (cta_group::2) form and the single-CTA form (flag RNC_CONV_NO_PAIR = 8) compute the same products in the
+    same order per accumulator: bit-identical outputs, including odd tile counts (ghost tile in the last pair) and the
+    hoisted-addend epilogue input."""
+    from rnc import native
+    from rnc.engine_umma import SplitBuf, UmmaWeights
+    g = torch.Generator().manual_seed(cin + cout + W)
+    x = torch.randn(B * H * W, cin, generator=g).to(DEV)
+    buf = SplitBuf(B * H * W, cin, DEV)
+    buf.hi[:], buf.lo[:] = split(x)
+    wt = UmmaWeights((torch.randn(cout, cin, kh, kw, generator=g) / (cin * kh * kw) ** 0.5).to(DEV), torch.randn(cout, generator=g).to(DEV), [cin])
+    add = torch.randn(B * H * W, wt.coutpad, generator=g).to(DEV)
+    outs = []
+    for flags in (0, 8):
+        out = torch.zeros(B * H * W, wt.coutpad, device=DEV)
+        ueng.uconv(B, H, W, buf.ptrs(), cin, cin, wt, native.EPI_RELU, out_f32=out.data_ptr(), ldo_f32=wt.coutpad,
+                   add=add.data_ptr(), ldadd=wt.coutpad, flags=flags)
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    # the addend really is added before the activation
+    out0 = torch.zeros_like(outs[0])
+    ueng.uconv(B, H, W, buf.ptrs(), cin, cin, wt, native.EPI_LINEAR, out_f32=out0.data_ptr(), ldo_f32=wt.coutpad)
+    assert (torch.relu(out0 + add)[:, :cout] - outs[0][:, :cout]).abs().max().item() < 1e-5
+
+
 def test_umma_two_segment_input(ueng):
     # q-gate convolution: input = cat(r*h [128], x [256]) read from two buffers (update.py:49)
     from rnc import native
