@@ -33,7 +33,7 @@ typedef enum {
 } rnc_status;
 
 /* Library identity / diagnostics. */
-int rnc_abi_version(void);                 /* bumps on any signature change (now 7) */
+int rnc_abi_version(void);                 /* bumps on any signature change (now 8) */
 const char* rnc_build_info(void);          /* e.g. "sm_100a nvcc 12.9" */
 const char* rnc_status_string(int status);
 int rnc_last_cuda_error(void);             /* cudaError_t of the last failed launch on this thread */
@@ -119,6 +119,8 @@ typedef enum {
 /* rnc_conv_umma_desc.flags */
 #define RNC_CONV_NO_HALO 1          /* force one A tile per filter tap (disable the row/column halo sharing) */
 #define RNC_CONV_BASE_OFFSET 2      /* debug: set the descriptor base_offset for row-shifted taps (wrong on B200) */
+#define RNC_CONV_AUX_BLOCKED 16     /* aux0 (z gate) and add are tile-blocked: element (tile, channel c, row r) at ((tile*ld + c)*128 + r) */
+#define RNC_CONV_OUT_BLOCKED 32     /* RNC_EPI_LINEAR: out_f32 in the same tile-blocked layout (produces an `add` operand)          */
 #define RNC_CONV_NO_PAIR 8          /* never use the CTA-pair (cta_group::2) form for this call */
 #define RNC_CONV_SPLIT_N 4          /* 256-column layers as two 128-column items per pixel tile (double-buffered TMEM) */
 
@@ -170,6 +172,9 @@ typedef struct {
                                         * hoisted contribution of input channels that do not change between calls */
 } rnc_conv_umma_desc;
 
+/* Pixel tiles (128 output pixels each) a layer of this shape is cut into: a tile-blocked tensor with ld channels has
+ * rnc_conv_umma_tiles(...) * ld * 128 floats; the tiling depends on (kh, kw, stride, H, W, flags & RNC_CONV_NO_HALO) only. */
+long long rnc_conv_umma_tiles(int kh, int kw, int stride, int B, int H, int W, int flags);
 int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream);
 
 /* fp32 CL [M][lds] channels [0,C) -> split halves planes [M][ldd] at channel offset ch_off (hi + lo == value exactly

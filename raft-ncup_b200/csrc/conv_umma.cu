@@ -44,6 +44,7 @@ struct Params {
   float* aux0; int ldaux;
   const float* res; int ldres;
   const float* add; int ldadd;        // optional fp32 addend of the pre-activation, [pixel][ldadd]
+  int aux_blocked, out_blocked;       // aux0 + add / out_f32 in the tile-blocked layout [tile][channel][128 px] (coalesced for thread = pixel)
   double* stats;                      // [B][cout][2]: per-(image, channel) sum / sum of squares of the outputs, accumulated
 };
 
@@ -307,6 +308,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
       if (use_stats && !ghost && (b != acc_b || n0 != acc_n0)) { flush_stats(); acc_b = b; acc_n0 = n0; }
       const int y = (tr / p.tiles_x) * p.TH + ml / p.TW, x = (tr % p.tiles_x) * p.TW + ml % p.TW;
       const bool valid = !ghost && y < p.H && x < p.W;
+      // tile-blocked tensors (p.aux_blocked / p.out_blocked): element (tile, channel c, row ml) at ((tile * ld + c) * 128 + ml),
+      // so a warp's 32 pixels are contiguous per channel
       const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
       const int buf = t_it % C::kBufs, use = t_it / C::kBufs;
       mbar_wait(&acc_full[buf], use & 1);
@@ -332,11 +335,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
         }
         if (p.add != nullptr && valid) {
           // hoisted part of the layer (input channels that are constant across calls), computed once by another launch
-          const float4* ap = reinterpret_cast<const float4*>(p.add + pix * p.ldadd + n);
+          if (p.aux_blocked) {
+            const float* ap = p.add + (static_cast<size_t>(tile) * p.ldadd + n) * kBM + ml;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 a = __ldg(ap + q);
-            v[4 * q] += a.x; v[4 * q + 1] += a.y; v[4 * q + 2] += a.z; v[4 * q + 3] += a.w;
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(ap + static_cast<size_t>(j) * kBM);
+          } else {
+            const float4* ap = reinterpret_cast<const float4*>(p.add + pix * p.ldadd + n);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 a = __ldg(ap + q);
+              v[4 * q] += a.x; v[4 * q + 1] += a.y; v[4 * q + 2] += a.z; v[4 * q + 3] += a.w;
+            }
           }
         }
         if (use_stats) {
@@ -355,10 +364,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
         if (epi == RNC_EPI_GRU_ZR) {
           const int Ch = p.cout >> 1;
           if (n < Ch) {            // z gate -> fp32 aux buffer
-            float4* dst = reinterpret_cast<float4*>(p.aux0 + pix * p.ldaux + n);
+            if (p.aux_blocked) {
+              float* dst = p.aux0 + (static_cast<size_t>(tile) * p.ldaux + n) * kBM + ml;
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-              dst[q] = make_float4(sigmoid_fast(v[4 * q]), sigmoid_fast(v[4 * q + 1]), sigmoid_fast(v[4 * q + 2]), sigmoid_fast(v[4 * q + 3]));
+              for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(j) * kBM] = sigmoid_fast(v[j]);
+            } else {
+              float4* dst = reinterpret_cast<float4*>(p.aux0 + pix * p.ldaux + n);
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                dst[q] = make_float4(sigmoid_fast(v[4 * q]), sigmoid_fast(v[4 * q + 1]), sigmoid_fast(v[4 * q + 2]), sigmoid_fast(v[4 * q + 3]));
+            }
           } else {                 // r gate -> r*h as split halves
             const float4* hp = reinterpret_cast<const float4*>(p.h + pix * p.ldh + (n - Ch));
             float4 hreg[8];        // all loads first (h is read-only here): no load->store serialisation
@@ -388,11 +403,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
         }
         bool want_f32 = p.out_f32 != nullptr;
         if (epi == RNC_EPI_GRU_Q) {
-          const float4* zp = reinterpret_cast<const float4*>(p.aux0 + pix * p.ldaux + n);
           float4* hp = reinterpret_cast<float4*>(p.h + pix * p.ldh + n);
           float4 zreg[8], hreg[8];   // issue every load before the first store (hp is read-modify-write)
+          if (p.aux_blocked) {
+            const float* zb = p.aux0 + (static_cast<size_t>(tile) * p.ldaux + n) * kBM + ml;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) { zreg[q] = __ldg(zp + q); hreg[q] = hp[q]; }
+            for (int q = 0; q < 8; ++q)
+              zreg[q] = make_float4(__ldg(zb + static_cast<size_t>(4 * q) * kBM), __ldg(zb + static_cast<size_t>(4 * q + 1) * kBM),
+                                    __ldg(zb + static_cast<size_t>(4 * q + 2) * kBM), __ldg(zb + static_cast<size_t>(4 * q + 3) * kBM));
+          } else {
+            const float4* zp = reinterpret_cast<const float4*>(p.aux0 + pix * p.ldaux + n);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) zreg[q] = __ldg(zp + q);
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) hreg[q] = hp[q];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 z = zreg[q], hv = hreg[q];
@@ -444,9 +469,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
           }
         }
         if (want_f32) {
-          float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.ldo_f32 + n);
+          if (p.out_blocked) {
+            float* dst = p.out_f32 + (static_cast<size_t>(tile) * p.ldo_f32 + n) * kBM + ml;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(j) * kBM] = v[j];
+          } else {
+            float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.ldo_f32 + n);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
         }
         if (p.out_hi) {
           uint4* dh = reinterpret_cast<uint4*>(p.out_hi + pix * p.ldo_split + n);
@@ -565,6 +596,20 @@ static bool pair_enabled() {
 }  // namespace rnc
 
 using namespace rnc;
+
+// Pixel-tile shape of a layer (the A-staging mode decides it): row halo -> 128x1, column halo -> 16x8, per-tap -> TW x 128/TW.
+static void tile_shape(int kh, int kw, int stride, int H, int W, int flags, int& TW, int& TH) {
+  if (stride == 1 && (flags & RNC_CONV_NO_HALO) == 0 && kw > 1 && W > 64) { TW = 128; TH = 1; }
+  else if (stride == 1 && (flags & RNC_CONV_NO_HALO) == 0 && kw == 1 && kh > 1 && W >= 16 && H >= 8) { TW = 16; TH = 8; }
+  else { TW = 8; while (TW < W && TW < umma::kBM) TW <<= 1; TH = umma::kBM / TW; }
+}
+
+extern "C" long long rnc_conv_umma_tiles(int kh, int kw, int stride, int B, int H, int W, int flags) {
+  if (kh <= 0 || kw <= 0 || stride <= 0 || B <= 0 || H <= 0 || W <= 0) return 0;
+  int TW, TH;
+  tile_shape(kh, kw, stride, H, W, flags, TW, TH);
+  return static_cast<long long>(B) * ((W + TW - 1) / TW) * ((H + TH - 1) / TH);
+}
 
 // Column-tile width.  The widest tile that divides coutpad is the default; a narrower one (more, smaller work items per
 // pixel tile) wins when the grid is under-filled (small batches: 56 pixel tiles on 148 SMs), when the tile count just
@@ -694,6 +739,10 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   p.h = d.h; p.ldh = d.ldh; p.aux0 = d.aux0; p.ldaux = d.ldaux; p.res = d.res; p.ldres = d.ldres;
   p.stats = d.stats;
   p.add = d.add; p.ldadd = d.ldadd;
+  p.aux_blocked = (d.flags & RNC_CONV_AUX_BLOCKED) ? 1 : 0;
+  p.out_blocked = (d.flags & RNC_CONV_OUT_BLOCKED) ? 1 : 0;
+  if (p.out_blocked && (d.epilogue != RNC_EPI_LINEAR || d.out_hi || d.stats)) return RNC_ERR_UNSUPPORTED;
+  if (p.aux_blocked && d.epilogue != RNC_EPI_GRU_ZR && d.epilogue != RNC_EPI_GRU_Q) return RNC_ERR_UNSUPPORTED;
 
   CUtensorMap maps[6];
   bool ok = make_in_map(&maps[0], d.in0_hi, d.c0, d.ld0, d.B, Hin, Win, box_w, box_h, stride) &&

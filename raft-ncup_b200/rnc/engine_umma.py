@@ -142,10 +142,15 @@ class UmmaWorkspace:
         self.hx = SplitBuf(M, HX_LD, device)
         self.rh = SplitBuf(M, 128, device)
         self.h = torch.zeros(M, 128, **f)            # fp32 master copy of the GRU state
-        self.z = torch.empty(M, 128, **f)
-        # hoisted context-feature share of the GRU gate pre-activations (valid until inp changes)
-        self.czr1, self.czr2 = torch.empty(M, 256, **f), torch.empty(M, 256, **f)
-        self.cq1, self.cq2 = torch.empty(M, 128, **f), torch.empty(M, 128, **f)
+        # Epilogue-only tensors live in the tile-blocked layout [tile][channel][128 px] of their layer's tiling (thread = pixel
+        # then reads / writes full lines): the z gate, and the hoisted context-feature share of the GRU gate pre-activations
+        # (valid until inp changes).  Horizontal (1x5) and vertical (5x1) layers tile differently; z serves both halves.
+        L = native.lib()
+        th = max(L.rnc_conv_umma_tiles(1, 5, 1, B, H8, W8, fl) for fl in (0, 1))      # with / without halo sharing (RNC_CONV_FLAGS)
+        tv = max(L.rnc_conv_umma_tiles(5, 1, 1, B, H8, W8, fl) for fl in (0, 1))
+        self.z = torch.empty(max(th, tv) * 128 * 128, **f)
+        self.czr1, self.czr2 = torch.empty(th * 256 * 128, **f), torch.empty(tv * 256 * 128, **f)
+        self.cq1, self.cq2 = torch.empty(th * 128 * 128, **f), torch.empty(tv * 128 * 128, **f)
         self.gru_const_valid = False
         self.fh = SplitBuf(M, 256, device)
         self.fh2p = torch.empty(M, 32, **f)      # FlowHead.conv2 per-tap partial sums
@@ -183,6 +188,8 @@ class UmmaEngine(Engine):
         self.convf1_mode = os.environ.get("RNC_CONVF1", "mm").lower()
         if self.convf1_mode not in ("mm", "ffma"):
             raise ValueError(f"RNC_CONVF1={self.convf1_mode!r}: expected 'mm' or 'ffma'")
+        # RNC_BLOCKED=0: keep the z gate / hoisted addends channel-last instead of tile-blocked (developer A/B switch)
+        self.blocked = os.environ.get("RNC_BLOCKED", "1") != "0"
         self.fork_convf1 = self.convf1_mode == "ffma" and os.environ.get("RNC_FORK", "1") != "0"
         self._side = None
 
@@ -324,15 +331,16 @@ class UmmaEngine(Engine):
         if not ws.gru_const_valid:
             # the context channels' share of the gate pre-activations (+ biases): once per forward
             for wt, buf in ((pk.zr1_c, ws.czr1), (pk.q1_c, ws.cq1), (pk.zr2_c, ws.czr2), (pk.q2_c, ws.cq2)):
-                self.uconv(B, H, W, ws.hx.ptrs(128), 128, HX_LD, wt, E.EPI_LINEAR, out_f32=buf.data_ptr(), ldo_f32=wt.coutpad)
+                self.uconv(B, H, W, ws.hx.ptrs(128), 128, HX_LD, wt, E.EPI_LINEAR, out_f32=buf.data_ptr(), ldo_f32=wt.coutpad,
+                           flags=self.conv_flags | (E.CONV_OUT_BLOCKED if self.blocked else 0))
             ws.gru_const_valid = True
         for zr, q, czr, cq in ((pk.zr1, pk.q1, ws.czr1, ws.cq1), (pk.zr2, pk.q2, ws.czr2, ws.cq2)):
             self.uconv(B, H, W, ws.hx.ptrs(), 128, HX_LD, zr, E.EPI_GRU_ZR, in1=ws.hx.ptrs(256), c1=128, ld1=HX_LD,
                        out_split=ws.rh.ptrs(), ldo_split=128, h=hp, ldh=128, aux0=ws.z.data_ptr(), ldaux=128,
-                       add=czr.data_ptr(), ldadd=256)
+                       add=czr.data_ptr(), ldadd=256, flags=self.conv_flags | (E.CONV_AUX_BLOCKED if self.blocked else 0))
             self.uconv(B, H, W, ws.rh.ptrs(), 128, 128, q, E.EPI_GRU_Q, in1=ws.hx.ptrs(256), c1=128, ld1=HX_LD,
                        out_split=ws.hx.ptrs(), ldo_split=HX_LD, h=hp, ldh=128, aux0=ws.z.data_ptr(), ldaux=128,
-                       add=cq.data_ptr(), ldadd=128)
+                       add=cq.data_ptr(), ldadd=128, flags=self.conv_flags | (E.CONV_AUX_BLOCKED if self.blocked else 0))
         # FlowHead (update.py:13-14) + coords1 += delta (raft_nc_dbl.py:157)
         self.uconv(B, H, W, ws.hx.ptrs(), 128, HX_LD, pk.fh1, E.EPI_RELU, out_split=ws.fh.ptrs(), ldo_split=256)
         self.uconv(B, H, W, ws.fh.ptrs(), 256, 256, pk.fh2, E.EPI_LINEAR, out_f32=ws.fh2p.data_ptr(), ldo_f32=32)
