@@ -64,6 +64,13 @@ def test_cabi_exports_every_declared_symbol():
     assert L.rnc_status_string(-1) == b"bad shape"
     # pure host helper: pyramid offsets (55x128 -> 27x64 -> 13x32 -> 6x16, floor mode)
     assert L.rnc_pyramid_offset(8, 256, 55, 128, 4) == 8 * 256 * (55 * 128 + 27 * 64 + 13 * 32 + 6 * 16)
+    # pure host helper: pixel tiles of a tensor-core layer (sizes the tile-blocked epilogue tensors)
+    assert L.rnc_conv_umma_tiles(1, 5, 1, 8, 55, 128, 0) == 8 * 55            # row halo: 128x1 tiles
+    assert L.rnc_conv_umma_tiles(5, 1, 1, 8, 55, 128, 0) == 8 * 8 * 7         # column halo: 16x8 tiles
+    assert L.rnc_conv_umma_tiles(5, 1, 1, 8, 55, 128, 1) == 8 * 55            # halo sharing off: 128x1 per-tap tiles
+    assert L.rnc_conv_umma_tiles(3, 3, 2, 2, 110, 256, 0) == 2 * 110 * 2      # stride 2: per-tap tiles
+    assert L.rnc_conv_umma_tiles(3, 3, 1, 1, 16, 32, 0) == 4                  # narrow image: 32x4 tiles
+    assert L.rnc_conv_umma_tiles(0, 3, 1, 1, 16, 32, 0) == 0
 
 
 def test_conv_desc_layout_matches_header():
