@@ -84,6 +84,31 @@ def test_conv_desc_layout_matches_header():
     assert order == names
 
 
+def test_umma_conv_desc_layout_matches_header():
+    """ctypes mirror of rnc_conv_umma_desc: same member names in the same order as include/rnc.h (and the same size as a C
+    compiler lays it out: pointers 8-aligned, ints packed)."""
+    from rnc.native import UmmaConvDesc
+    names = [f[0] for f in UmmaConvDesc._fields_]
+    hdr = open(os.path.join(ROOT, "include", "rnc.h")).read()
+    end = hdr.index("} rnc_conv_umma_desc;")
+    body = hdr[hdr.rindex("typedef struct {", 0, end):end]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    order = []
+    for decl in body.split(";"):
+        decl = decl.replace("typedef struct {", "").strip()
+        if not decl:
+            continue
+        for part in decl.split(","):
+            order.append(re.findall(r"[A-Za-z_][A-Za-z0-9_]*", part)[-1])
+    assert order == names
+    import ctypes
+    expect = 0
+    for _, t in UmmaConvDesc._fields_:
+        a = ctypes.alignment(t)
+        expect = (expect + a - 1) // a * a + ctypes.sizeof(t)
+    assert ctypes.sizeof(UmmaConvDesc) == (expect + 7) // 8 * 8
+
+
 def test_cpu_tensors_fail_loudly_no_fallback():
     from rnc.native import RncUnavailable
     m = build_model("raft_nc_dbl")
