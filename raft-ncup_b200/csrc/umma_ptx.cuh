@@ -147,8 +147,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_saddr, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(rank));
   return r;
 }
+// Default semantics (release at CTA scope): the barrier only has to order this thread's TMEM reads (tcgen05.wait::ld +
+// fence::before_thread_sync) before the leader's next MMA; a cluster-scope release compiles to MEMBAR.ALL.GPU and makes the
+// epilogue warp wait for all of its global stores to drain at every tile (6 % of the q-gate layer's stall samples).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
   asm volatile(
