@@ -33,7 +33,7 @@ typedef enum {
 } rnc_status;
 
 /* Library identity / diagnostics. */
-int rnc_abi_version(void);                 /* bumps on any signature change (now 8) */
+int rnc_abi_version(void);                 /* bumps on any signature change (now 9) */
 const char* rnc_build_info(void);          /* e.g. "sm_100a nvcc 12.9" */
 const char* rnc_status_string(int status);
 int rnc_last_cuda_error(void);             /* cudaError_t of the last failed launch on this thread */
@@ -287,6 +287,36 @@ int rnc_conf_head_fwd(const float* in, int cin, int ldi, const float* weight, co
  */
 int rnc_ncup_fwd(const float* x_lowres, const float* conf, const float* wts_host, int B, int H4, int W4,
                  float out_scale, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A3  bilinear_sampler  (core/utils/utils.py:59-73) as a standalone operator: grid_sample(align_corners=True, bilinear,
+ * zero padding) with the grid in pixel coordinates.  img NCHW [N][C][H][W]; coords [N][h][w][2] = (x, y); out NCHW
+ * [N][C][h][w]; mask (optional, may be NULL) [N][h][w][1] as utils.py:69-71.  H, W >= 2 (the reference divides by W-1).
+ */
+int rnc_bilinear_sample_fwd(const float* img, const float* coords, int N, int C, int H, int W, int h, int w,
+                            float* out, float* mask, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * U6  NConv2d.forward  (core/nconv_modules.py:164-199) — ONE normalized-convolution layer, the operator seam
+ *     `NConv2d((data, conf)) -> (y, conf_out)`, and the per-layer form the training path differentiates through
+ *     (the inference path runs the fused chain rnc_ncup_fwd instead).
+ *   data, conf : NCHW [N][Cin][H][W] fp32;  weight: [Cout][Cin][kh][kw] fp32 = softplus_{beta=10}(weight_p)
+ *                (nconv_modules.py:250-264; the caller applies it), zero padding k/2, stride 1, no bias
+ *   y = conv(data*conf, W) / (conv(conf, W) + eps),   conf_out = conv(conf, W) / sum_{i,ky,kx} W[o]
+ * Supported: Cin, Cout <= 4, odd kh, kw <= 7.
+ */
+int rnc_nconv2d_fwd(const float* data, const float* conf, const float* weight, int N, int Cin, int Cout, int H, int W,
+                    int kh, int kw, float eps, float* y, float* conf_out, void* stream);
+/* Backward of rnc_nconv2d_fwd (autograd of nconv_modules.py:169-194: quotient rule through num/(den+eps), confidence
+ * propagation incl. its dependence on sum(W)).  g_y / g_conf_out: upstream gradients (either may be NULL = zero);
+ * g_data, g_conf, g_weight ([Cout][Cin][kh][kw], w.r.t. the POSITIVE kernel; the caller chains softplus'): outputs, each
+ * may be NULL.  workspace: rnc_nconv2d_bwd_workspace_bytes(N,Cout,H,W) bytes, ZERO-INITIALISED by the caller before its
+ * first use (the call leaves its accumulators zeroed again). */
+size_t rnc_nconv2d_bwd_workspace_bytes(int N, int Cout, int H, int W);
+int rnc_nconv2d_bwd(const float* data, const float* conf, const float* weight, const float* y, const float* conf_out,
+                    const float* g_y, const float* g_conf_out, int N, int Cin, int Cout, int H, int W, int kh, int kw,
+                    float eps, float* g_data, float* g_conf, float* g_weight, void* workspace, size_t workspace_bytes,
+                    void* stream);
 
 #ifdef __cplusplus
 }

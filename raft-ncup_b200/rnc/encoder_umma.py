@@ -79,17 +79,10 @@ class EncoderRunner:
     def __init__(self, engine):
         self.eng = engine
         self.L = engine.L
-        self._packed = {}
         self._bufs = None
 
     def packed(self, enc):
-        from .engine import _param_key
-        key = _param_key(enc)
-        hit = self._packed.get(id(enc))
-        if hit is None or hit[0] != key:
-            hit = (key, PackedEncoder(enc))
-            self._packed[id(enc)] = hit
-        return hit[1]
+        return self.eng._packed_for("enc", enc, PackedEncoder)
 
     def buffers(self, device, N, Hin, Win):
         if self._bufs is None or self._bufs.key != (str(device), N, Hin, Win):

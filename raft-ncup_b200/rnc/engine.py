@@ -10,6 +10,9 @@ PyTorch is used here only as plumbing: device memory (torch.empty), the current 
 re-packing at load time.  All arithmetic of the path runs in librnc.so; there is no fallback.
 """
 import ctypes as C
+import os
+import threading
+from collections import OrderedDict
 
 import torch
 import torch.nn.functional as F
@@ -30,10 +33,38 @@ def _ptr(t):
 
 
 def _require_cuda(*tensors):
+    """Every tensor must live on one CUDA device (returned).  The kernels are launched on that device's current stream
+    (callers wrap the launches in ``torch.cuda.device(dev)``), never on whatever device happens to be current."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise native.RncUnavailable(
                 "the RAFT-NCUP hot path runs only on CUDA (sm_100a) tensors; got a CPU tensor and there is no CPU fallback")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ValueError(f"tensors on different CUDA devices ({dev} and {t.device}): move them to one device first")
+    return dev
+
+
+def module_tensors(module):
+    """Parameters and buffers a module tree computes with, also for nn.DataParallel replicas: a replica has empty
+    ``_parameters`` and carries its per-device broadcast copies in ``_former_parameters`` (torch/nn/parallel/replicate.py)."""
+    out = []
+    for m in module.modules():
+        out.extend(p for p in m._parameters.values() if p is not None)
+        if getattr(m, "_is_replica", False):
+            out.extend(p for p in getattr(m, "_former_parameters", {}).values() if p is not None)
+        out.extend(b for b in m._buffers.values() if b is not None)
+    return out
+
+
+def module_device(module):
+    for t in module_tensors(module):
+        return t.device
+    return None
 
 
 def pack_conv(weight, bias, cin_pad=None, scale=1.0):
@@ -55,22 +86,41 @@ def pack_thin(weight):
     return weight.detach().float().permute(2, 3, 1, 0).reshape(kh * kw, cin, cout).contiguous()
 
 
-class PackedUpdateBlock:
-    """Kernel-ready weights of BasicUpdateBlock (update.py:114-128)."""
+class PackedMotionEncoder:
+    """Kernel-ready weights of BasicMotionEncoder (update.py:79-87) for the exact fp32 CUDA-core kernels."""
 
-    def __init__(self, ub):
-        e, g, fh = ub.encoder, ub.gru, ub.flow_head
+    def __init__(self, e):
         self.convc1 = pack_conv(e.convc1.weight, e.convc1.bias)
         self.convc2 = pack_conv(e.convc2.weight, e.convc2.bias)
         self.convf1 = (pack_thin(e.convf1.weight), e.convf1.bias.detach().float().contiguous())
         self.convf2 = pack_conv(e.convf2.weight, e.convf2.bias)
         self.conv = pack_conv(e.conv.weight, e.conv.bias)
+
+
+class PackedGRU:
+    """SepConvGRU (update.py:33-43): z and r of each half step share one 256-column layer."""
+
+    def __init__(self, g):
         self.zr1 = pack_conv(torch.cat([g.convz1.weight, g.convr1.weight], 0), torch.cat([g.convz1.bias, g.convr1.bias], 0))
         self.q1 = pack_conv(g.convq1.weight, g.convq1.bias)
         self.zr2 = pack_conv(torch.cat([g.convz2.weight, g.convr2.weight], 0), torch.cat([g.convz2.bias, g.convr2.bias], 0))
         self.q2 = pack_conv(g.convq2.weight, g.convq2.bias)
+
+
+class PackedFlowHead:
+    """FlowHead (update.py:6-11)."""
+
+    def __init__(self, fh):
         self.fh1 = pack_conv(fh.conv1.weight, fh.conv1.bias)
         self.fh2 = (pack_thin(fh.conv2.weight), fh.conv2.bias.detach().float().contiguous())
+
+
+class PackedUpdateBlock:
+    """Kernel-ready weights of BasicUpdateBlock (update.py:114-128)."""
+
+    def __init__(self, ub):
+        for part in (PackedMotionEncoder(ub.encoder), PackedGRU(ub.gru), PackedFlowHead(ub.flow_head)):
+            self.__dict__.update(part.__dict__)
         self.has_mask = len(ub.mask) > 0
         if self.has_mask:
             self.m0 = pack_conv(ub.mask[0].weight, ub.mask[0].bias)
@@ -106,8 +156,37 @@ class PackedUpsampler:
         self.nconv_host = (C.c_float * 224)(*host.tolist())
 
 
+def _checksum(tensors):
+    """Content checksum (one device sync): exact int64 sum of the fp32 bit patterns, position-weighted per tensor."""
+    acc = None
+    for i, t in enumerate(tensors):
+        v = t.detach().reshape(-1)
+        v = v.view(torch.int32) if v.dtype == torch.float32 else v.to(torch.int64)
+        part = v.sum(dtype=torch.int64) * (2 * i + 1)
+        acc = part if acc is None else acc + part
+    return int(acc.item()) if acc is not None else 0
+
+
 def _param_key(module):
-    return tuple((p.data_ptr(), p._version) for p in list(module.parameters()) + list(module.buffers()))
+    """Staleness key of a module's packed weights.  Ordinary modules: (storage pointer, version counter) of every parameter
+    and buffer — load_state_dict, optimizer steps, .to() all change it.  In-place edits through ``.data`` bypass the version
+    counter: call ``invalidate_packed()`` after them, or set RNC_PARAM_CHECK=checksum to key on the contents instead (costs
+    one device sync per forward).  DataParallel replicas get fresh broadcast copies every forward (same addresses may hold
+    new values), so they are always keyed by content."""
+    ts = module_tensors(module)
+    replica = any(getattr(m, "_is_replica", False) for m in module.modules())
+    dev = str(ts[0].device) if ts else ""
+    if replica or os.environ.get("RNC_PARAM_CHECK", "") == "checksum":
+        return ("sum", dev, len(ts), _checksum(ts))
+    return ("ptr", dev, _EPOCH[0]) + tuple((p.data_ptr(), p._version) for p in ts)
+
+
+_EPOCH = [0]
+
+
+def invalidate_packed():
+    """Force every engine to re-pack weights on the next forward (needed only after in-place edits through ``.data``)."""
+    _EPOCH[0] += 1
 
 
 class Workspace:
@@ -161,10 +240,34 @@ class _Timed:
         return False
 
 
+_ENGINES = {}
+_ENGINES_LOCK = threading.Lock()
+_ENGINE_ENV = ("RNC_CONV", "RNC_LOOKUP", "RNC_CONVF1", "RNC_FORK", "RNC_BLOCKED", "RNC_CONV_FLAGS")
+
+
+def engine_for(device):
+    """The engine of one CUDA device.  Engines (packed weights, workspaces, side streams) are per-device process-wide state
+    that lives OUTSIDE the nn.Modules: modules stay deep-copyable / picklable, and nn.DataParallel replicas (one thread per
+    device, shallow-copied module __dict__) never share packed weights or workspaces across devices."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise native.RncUnavailable("the RAFT-NCUP hot path runs only on CUDA (sm_100a) devices; there is no CPU fallback")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx,) + tuple(os.environ.get(k, "") for k in _ENGINE_ENV)      # developer switches select distinct engines
+    eng = _ENGINES.get(key)
+    if eng is None:
+        with _ENGINES_LOCK:
+            eng = _ENGINES.get(key)
+            if eng is None:
+                with torch.cuda.device(idx):
+                    eng = _ENGINES[key] = make_engine()
+                eng.device = torch.device("cuda", idx)
+    return eng
+
+
 def make_engine():
     """RNC_CONV=umma (default): tcgen05 tensor-core convolutions on fp16 hi/lo split operands;
     RNC_CONV=ffma: exact-fp32 CUDA-core convolutions (v1, kept as the on-GPU cross-check)."""
-    import os
     mode = os.environ.get("RNC_CONV", "umma").lower()
     if mode == "ffma":
         return Engine()
@@ -175,38 +278,50 @@ def make_engine():
 
 
 class Engine:
-    """Issues the kernels.  One per model instance; keeps packed weights and workspaces."""
+    """Issues the kernels.  One per CUDA device (engine_for); keeps packed weights and workspaces.  ``lock`` serialises the
+    forwards of one device (nn.DataParallel drives different devices from different threads: different engines)."""
     mode = "ffma"
+    PACK_UB, PACK_UP = PackedUpdateBlock, PackedUpsampler
+    WS = Workspace
+    MAX_WS, MAX_PACKED = 6, 64
 
     def __init__(self):
         self.profile = None
-        self._packed_ub = None
-        self._packed_up = None
-        self._ub_key = None
-        self._up_key = None
-        self._ws = {}
+        self._packed = OrderedDict()        # (kind, param key) -> packed weights, LRU
+        self._ws = OrderedDict()            # workspace key -> workspace, LRU
+        self.lock = threading.RLock()
+        self.device = None
         self.L = native.lib()
 
     # ------------------------------------------------------------------ caches
+    def _packed_for(self, kind, module, build):
+        key = (kind,) + _param_key(module)
+        hit = self._packed.get(key)
+        if hit is None:
+            hit = self._packed[key] = build(module)
+            while len(self._packed) > self.MAX_PACKED:
+                self._packed.popitem(last=False)
+        else:
+            self._packed.move_to_end(key)
+        return hit
+
     def packed_update(self, ub):
-        key = _param_key(ub)
-        if key != self._ub_key:
-            self._packed_ub, self._ub_key = PackedUpdateBlock(ub), key
-        return self._packed_ub
+        return self._packed_for("ub", ub, self.PACK_UB)
 
     def packed_upsampler(self, up):
-        key = _param_key(up)
-        if key != self._up_key:
-            self._packed_up, self._up_key = PackedUpsampler(up), key
-        return self._packed_up
+        return self._packed_for("up", up, self.PACK_UP)
 
     def workspace(self, device, B, H8, W8, with_mask, with_ncup):
-        key = (str(device), B, H8, W8, with_mask, with_ncup)
+        """Resident buffers for one problem shape.  The least recently used one is dropped when a fifth shape shows up; the
+        caller holds ``self.lock`` for the whole forward, so a workspace in use is never the one evicted."""
+        key = (self.mode, str(device), B, H8, W8, with_mask, with_ncup)
         ws = self._ws.get(key)
         if ws is None:
-            if len(self._ws) >= 4:
-                self._ws.clear()
-            ws = self._ws[key] = Workspace(device, B, H8, W8, with_mask, with_ncup)
+            while len(self._ws) >= self.MAX_WS:
+                self._ws.popitem(last=False)
+            ws = self._ws[key] = self.WS(device, B, H8, W8, with_mask, with_ncup)
+        else:
+            self._ws.move_to_end(key)
         return ws
 
     # ------------------------------------------------------------------ single kernels
@@ -261,33 +376,59 @@ class Engine:
             self._update_iter(ws, pk, want_mask, want_delta)
 
     def _update_iter(self, ws, pk, want_mask, want_delta):
+        self._motion_encoder_ffma(ws, pk)
+        self._gru_ffma(ws, pk)
+        self._flow_head_ffma(ws, pk, want_delta)
+        if want_mask:
+            # mask head (update.py:123-126,140), 0.25 folded into the 1x1 weights
+            B, H, W = ws.B, ws.H8, ws.W8
+            self.conv(B, H, W, ws.hx.data_ptr(), 128, HX_LD, pk.m0, 256, 3, 3, native.EPI_RELU, ws.mh.data_ptr(), 256)
+            self.conv(B, H, W, ws.mh.data_ptr(), 256, 256, pk.m2, 576, 1, 1, native.EPI_LINEAR, ws.mask.data_ptr(), 576)
+
+    # The three pieces below run the exact fp32 CUDA-core kernels on an `ffma` Workspace; they are the whole update block of
+    # the RNC_CONV=ffma engine and the bodies of the operator seams FlowHead / SepConvGRU / BasicMotionEncoder.forward.
+    def _motion_encoder_ffma(self, ws, pk):
+        """BasicMotionEncoder (update.py:89-97): ws.corr, ws.coords1 -> hx[:, 256:384] = [motion(126) | flow(2)]."""
         B, H, W = ws.B, ws.H8, ws.W8
-        s = _stream()
-        hx = ws.hx.data_ptr()
-        x_ptr = hx + 128 * 4          # channels 128.. = [inp | motion | flow]
-        mot_ptr = hx + 256 * 4
-        # BasicMotionEncoder (update.py:89-97)
+        mot_ptr = ws.hx.data_ptr() + 256 * 4
         self.conv(B, H, W, ws.corr.data_ptr(), CORR_CH, CORR_CH, pk.convc1, 256, 1, 1, native.EPI_RELU, ws.c1.data_ptr(), 256)
         self.conv(B, H, W, ws.c1.data_ptr(), 256, 256, pk.convc2, 192, 3, 3, native.EPI_RELU, ws.corflo.data_ptr(), 256)
         native.check(self.L.rnc_conv_flow7x7_fwd(_ptr(ws.coords1), _ptr(pk.convf1[0]), _ptr(pk.convf1[1]), B, H, W, 128,
-                                                 _ptr(ws.f1), 128, s), "convf1")
+                                                 _ptr(ws.f1), 128, _stream()), "convf1")
         self.conv(B, H, W, ws.f1.data_ptr(), 128, 128, pk.convf2, 64, 3, 3, native.EPI_RELU, ws.corflo.data_ptr() + 192 * 4, 256)
         self.conv(B, H, W, ws.corflo.data_ptr(), 256, 256, pk.conv, 126, 3, 3, native.EPI_RELU_FLOW, mot_ptr, HX_LD,
                   aux0=ws.coords1.data_ptr(), ldaux=0)
-        # SepConvGRU (update.py:45-60): horizontal (1x5) then vertical (5x1) half steps
+
+    def _gru_ffma(self, ws, pk):
+        """SepConvGRU (update.py:45-60): horizontal (1x5) then vertical (5x1) half steps on hx = [h | x]; h in place."""
+        B, H, W = ws.B, ws.H8, ws.W8
+        hx = ws.hx.data_ptr()
+        x_ptr = hx + 128 * 4          # channels 128.. = [inp | motion | flow]
         for zr, q, kh, kw in ((pk.zr1, pk.q1, 1, 5), (pk.zr2, pk.q2, 5, 1)):
             self.conv(B, H, W, hx, HX_LD, HX_LD, zr, 256, kh, kw, native.EPI_GRU_ZR, ws.rh.data_ptr(), 128,
                       h=hx, ldh=HX_LD, aux0=ws.z.data_ptr(), ldaux=128)
             self.conv(B, H, W, ws.rh.data_ptr(), 128, 128, q, 128, kh, kw, native.EPI_GRU_Q, in1=x_ptr, c1=256, ld1=HX_LD,
                       h=hx, ldh=HX_LD, aux0=ws.z.data_ptr(), ldaux=128)
-        # FlowHead (update.py:13-14) + coords1 += delta (raft_nc_dbl.py:157)
-        self.conv(B, H, W, hx, 128, HX_LD, pk.fh1, 256, 3, 3, native.EPI_RELU, ws.fh.data_ptr(), 256)
+
+    def _flow_head_ffma(self, ws, pk, want_delta):
+        """FlowHead (update.py:13-14) + coords1 += delta (raft_nc_dbl.py:157)."""
+        B, H, W = ws.B, ws.H8, ws.W8
+        self.conv(B, H, W, ws.hx.data_ptr(), 128, HX_LD, pk.fh1, 256, 3, 3, native.EPI_RELU, ws.fh.data_ptr(), 256)
         native.check(self.L.rnc_flow_head2_fwd(_ptr(ws.fh), 256, 256, _ptr(pk.fh2[0]), _ptr(pk.fh2[1]), B, H, W,
-                                               _ptr(ws.delta) if want_delta else C.c_void_p(0), _ptr(ws.coords1), s), "flow_head2")
-        if want_mask:
-            # mask head (update.py:123-126,140), 0.25 folded into the 1x1 weights
-            self.conv(B, H, W, hx, 128, HX_LD, pk.m0, 256, 3, 3, native.EPI_RELU, ws.mh.data_ptr(), 256)
-            self.conv(B, H, W, ws.mh.data_ptr(), 256, 256, pk.m2, 576, 1, 1, native.EPI_LINEAR, ws.mask.data_ptr(), 576)
+                                               _ptr(ws.delta) if want_delta else C.c_void_p(0), _ptr(ws.coords1), _stream()),
+                     "flow_head2")
+
+    def ffma_workspace(self, device, B, H8, W8, with_mask=False, with_ncup=False):
+        """Workspace of the exact fp32 CUDA-core kernels (operator seams), whatever this engine's own mode is."""
+        key = ("ffma", str(device), B, H8, W8, with_mask, with_ncup)
+        ws = self._ws.get(key)
+        if ws is None:
+            while len(self._ws) >= self.MAX_WS:
+                self._ws.popitem(last=False)
+            ws = self._ws[key] = Workspace(device, B, H8, W8, with_mask, with_ncup)
+        else:
+            self._ws.move_to_end(key)
+        return ws
 
     def load_state(self, ws, net, inp):
         """NCHW net/inp (raft_nc_dbl.py:137-140) -> resident hx buffer."""

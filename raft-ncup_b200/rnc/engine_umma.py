@@ -158,6 +158,7 @@ class UmmaWorkspace:
         self.coords1 = torch.empty(B, 2, H8, W8, **f)
         self.delta = torch.empty(B, 2, H8, W8, **f)
         self.f1_cl = self.f2_pyr = None
+        self.convf1_forked = False
         if with_mask:
             self.mh = SplitBuf(M, 256, device)
             self.mask = torch.empty(M, 576, **f)
@@ -173,6 +174,8 @@ class UmmaWorkspace:
 
 class UmmaEngine(Engine):
     mode = "umma"
+    PACK_UB, PACK_UP = PackedUpdateUmma, PackedUpsamplerUmma
+    WS = UmmaWorkspace
 
     def __init__(self):
         super().__init__()
@@ -192,29 +195,6 @@ class UmmaEngine(Engine):
         self.blocked = os.environ.get("RNC_BLOCKED", "1") != "0"
         self.fork_convf1 = self.convf1_mode == "ffma" and os.environ.get("RNC_FORK", "1") != "0"
         self._side = None
-
-    def packed_update(self, ub):
-        from .engine import _param_key
-        key = _param_key(ub)
-        if key != self._ub_key:
-            self._packed_ub, self._ub_key = PackedUpdateUmma(ub), key
-        return self._packed_ub
-
-    def packed_upsampler(self, up):
-        from .engine import _param_key
-        key = _param_key(up)
-        if key != self._up_key:
-            self._packed_up, self._up_key = PackedUpsamplerUmma(up), key
-        return self._packed_up
-
-    def workspace(self, device, B, H8, W8, with_mask, with_ncup):
-        key = ("umma", str(device), B, H8, W8, with_mask, with_ncup)
-        ws = self._ws.get(key)
-        if ws is None:
-            if len(self._ws) >= 4:
-                self._ws.clear()
-            ws = self._ws[key] = UmmaWorkspace(device, B, H8, W8, with_mask, with_ncup)
-        return ws
 
     # ------------------------------------------------------------------ one tensor-core convolution
     def uconv(self, B, H, W, in0, c0, ld0, wt, epi, out_f32=0, ldo_f32=0, out_split=(0, 0), ldo_split=0, in1=(0, 0), c1=0, ld1=0,

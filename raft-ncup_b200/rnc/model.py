@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import native
-from .engine import _Timed, _ptr, _require_cuda, _stream, make_engine
+from .engine import _Timed, _ptr, _require_cuda, _stream, engine_for, module_device, module_tensors
 from .modules import BasicEncoder, BasicUpdateBlock, get_upsampler
 
 
@@ -32,7 +32,6 @@ class _RAFTBase(nn.Module):
         self.fnet = BasicEncoder(output_dim=256, norm_fn="instance", dropout=args.dropout)
         self.cnet = BasicEncoder(output_dim=256, norm_fn="batch", dropout=args.dropout)
         self.update_block = BasicUpdateBlock(self.args, hidden_dim=128)
-        self._eng = None
 
     # ------------------------------------------------------------------ reference helpers kept verbatim in meaning
     def freeze_bn(self):
@@ -47,18 +46,28 @@ class _RAFTBase(nn.Module):
         g = torch.stack([xs, ys], 0).float()[None].repeat(N, 1, 1, 1)
         return g, g.clone()
 
-    def engine(self):
-        if self._eng is None:
-            self._eng = make_engine()
-        return self._eng
+    def engine(self, device=None):
+        """The per-device engine (rnc.engine.engine_for) this model's forwards run on.  Nothing is cached on the module:
+        it stays deep-copyable / picklable, and nn.DataParallel replicas resolve their own device's engine."""
+        return engine_for(device if device is not None else module_device(self))
 
     # ------------------------------------------------------------------ forward
     def _needs_grad(self):
-        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        return torch.is_grad_enabled() and any(t.requires_grad for t in module_tensors(self))
 
     def forward(self, image1, image2, iters=12, flow_init=None, upsample=True, test_mode=False):
         """Estimate optical flow between a pair of frames (raft_nc_dbl.py:115-173 / raft.py:87-143)."""
-        _require_cuda(image1, image2)
+        dev = _require_cuda(image1, image2, flow_init)
+        pdev = module_device(self)
+        if pdev != dev:
+            raise ValueError(f"model parameters are on {pdev} but the images are on {dev}")
+        eng = engine_for(dev)
+        # the kernels launch on `dev`'s current stream whatever device is current in the calling thread (nn.DataParallel
+        # worker threads, a model on cuda:1 in a cuda:0 process); one forward at a time per device
+        with torch.cuda.device(dev), eng.lock:
+            return self._forward(eng, image1, image2, iters, flow_init, test_mode)
+
+    def _forward(self, eng, image1, image2, iters, flow_init, test_mode):
         if self._needs_grad():
             raise NotImplementedError(
                 "training (autograd through the fused kernels) is not built yet (SURVEY.md §8f-3); "
@@ -71,7 +80,6 @@ class _RAFTBase(nn.Module):
         if Him % 8 or Wim % 8:
             raise ValueError("image height/width must be multiples of 8 (pad with utils.utils.InputPadder, evaluate.py:125)")
         H8, W8 = Him // 8, Wim // 8
-        eng = self.engine()
         L = eng.L
         pk = eng.packed_update(self.update_block)
         pu = eng.packed_upsampler(self.upsampler) if self.ncup else None
@@ -134,14 +142,15 @@ class RAFTConvex(_RAFTBase):
 
     def upsample_flow(self, flow, mask):
         """raft.py:73-84: flow [N,2,H8,W8], mask [N,576,H8,W8] (NCHW) -> [N,2,8*H8,8*W8]."""
-        _require_cuda(flow, mask)
-        eng = self.engine()
+        dev = _require_cuda(flow, mask)
+        eng = engine_for(dev)
         B, _, H8, W8 = flow.shape
-        m_cl = torch.empty(B * H8 * W8, 576, dtype=torch.float32, device=flow.device)
-        native.check(eng.L.rnc_nchw_to_cl(_ptr(mask.detach().float().contiguous()), B, 576, H8, W8, _ptr(m_cl), 576, 0, _stream()),
-                     "nchw_to_cl(mask)")
-        ws = _Dims(B, H8, W8)
-        return eng.convex_upsample(ws, flow.detach().float().contiguous(), m_cl, 576)
+        with torch.cuda.device(dev), eng.lock:
+            m_cl = torch.empty(B * H8 * W8, 576, dtype=torch.float32, device=dev)
+            native.check(eng.L.rnc_nchw_to_cl(_ptr(mask.detach().float().contiguous()), B, 576, H8, W8, _ptr(m_cl), 576, 0, _stream()),
+                         "nchw_to_cl(mask)")
+            ws = _Dims(B, H8, W8)
+            return eng.convex_upsample(ws, flow.detach().float().contiguous(), m_cl, 576)
 
 
 class RAFTNcup(_RAFTBase):

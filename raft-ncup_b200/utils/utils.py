@@ -45,6 +45,28 @@ def forward_interpolate(flow):
     return out[0] if squeeze else out
 
 
+def bilinear_sampler(img, coords, mode="bilinear", mask=False):
+    """utils.py:59-73 — grid_sample(align_corners=True) with pixel coordinates: img [N,C,H,W], coords [N,h,w,2] -> [N,C,h,w]
+    (and, with mask=True, the in-bounds mask [N,h,w,1]).  Runs librnc's sampler kernel; zero padding outside the image."""
+    from rnc import native
+    from rnc.engine import _require_cuda
+    if mode != "bilinear":
+        raise NotImplementedError("only bilinear sampling is built (the reference never passes another mode)")
+    dev = _require_cuda(img, coords)
+    N, Cc, H, W = img.shape
+    if coords.dim() != 4 or coords.shape[0] != N or coords.shape[-1] != 2:
+        raise ValueError("coords must be [N,h,w,2]")
+    h, w = coords.shape[1:3]
+    with torch.cuda.device(dev):
+        out = torch.empty(N, Cc, h, w, dtype=torch.float32, device=dev)
+        m = torch.empty(N, h, w, 1, dtype=torch.float32, device=dev) if mask else None
+        native.check(native.lib().rnc_bilinear_sample_fwd(
+            C.c_void_p(img.detach().float().contiguous().data_ptr()), C.c_void_p(coords.detach().float().contiguous().data_ptr()),
+            N, Cc, H, W, h, w, C.c_void_p(out.data_ptr()), C.c_void_p(m.data_ptr() if mask else 0),
+            C.c_void_p(torch.cuda.current_stream().cuda_stream)), "bilinear_sampler")
+    return (out, m) if mask else out
+
+
 def coords_grid(batch, ht, wd):
     ys, xs = torch.meshgrid(torch.arange(ht), torch.arange(wd), indexing="ij")
     return torch.stack([xs, ys], 0).float()[None].repeat(batch, 1, 1, 1)
