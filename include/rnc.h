@@ -76,7 +76,10 @@ int rnc_corr_lookup_split_fwd(const float* f1_cl, const float* f2_pyr, const flo
                               void* out_hi, void* out_lo, int ldo, int lvl_stride, void* stream);
 /* lvl_stride: channels reserved per pyramid level in the output row (>= 81; level l starts at l*lvl_stride, the
  * channels [81, lvl_stride) of each level are written as zeros).  The tensor-core path uses 88 so that every 8-channel
- * group is one aligned 16-byte store and convc1's K stays 6 blocks of 64. */
+ * group is one aligned 16-byte store and convc1's K stays 6 blocks of 64.
+ * Channel order of the split planes inside a level ("resident order"; only convc1 consumes them, with its weight rows
+ * permuted to match): tap (i, j) -> j*8 + i for i < 8, tap (8, j) -> 72 + j  — a pixel's 8 values of one window row are
+ * one aligned 16-byte group.  The reference order k = i*9 + j is what rnc_corr_lookup_fwd returns. */
 
 /* Tensor-core version of the lookup (tcgen05 + TMA; same reference code, corr.py:7-55 + utils.py:59-73).
  *   f1h_cl / f2h_pyr : the CL feature map / pyramid of rnc_fmap_prepare rounded once to halves (rnc_f32_to_f16), same
@@ -91,7 +94,8 @@ size_t rnc_corr_lookup_umma_workspace_bytes(int B, int H, int W);
 int rnc_corr_lookup_umma_fwd(const void* f1h_cl, const void* f2h_pyr, const float* f1_cl, const float* f2_pyr,
                              const float* coords, int B, int D, int H, int W, int levels, int radius,
                              void* out_hi, void* out_lo, int ldo, int lvl_stride, void* workspace, size_t workspace_bytes,
-                             void* stream);   /* lvl_stride must be 88 */
+                             void* stream);   /* lvl_stride must be 88; resident channel order (above); out_hi/out_lo
+                                                 16-byte aligned, ldo % 8 == 0: the tiles leave through TMA stores */
 /* fp32 -> fp16 (round to nearest), n % 4 == 0. */
 int rnc_f32_to_f16(const float* src, void* dst, size_t n, void* stream);
 

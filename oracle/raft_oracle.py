@@ -305,13 +305,14 @@ def basic_encoder(sd, p, x, kind):
 # --------------------------------------------------------------------------- A9: the model loop
 
 
-@torch.no_grad()
-def raft_forward(sd, image1, image2, iters=12, model="raft_nc_dbl", flow_init=None, use_bn=True,
-                 upsample_every_iter=True, trace=None):
+def raft_forward_graph(sd, image1, image2, iters=12, model="raft_nc_dbl", flow_init=None, use_bn=True,
+                       upsample_every_iter=True, trace=None):
     """core/raft_nc_dbl.py:115-173 (model='raft_nc_dbl') / core/raft.py:87-143 (model='raft').
     Returns (flow_low, flow_up_last, [flow_up per iter]).  `trace`, if a dict, receives teacher-forcing
     tensors.  upsample_every_iter=False skips the (result-irrelevant) per-iteration NCUP calls the
-    reference makes in test_mode (raft_nc_dbl.py:161)."""
+    reference makes in test_mode (raft_nc_dbl.py:161).
+    Differentiable when the tensors of `sd` require grad (training oracle, train.py:215: BatchNorm in eval mode as after
+    freeze_bn(), train.py:185-186); `coords1` is detached at the top of every iteration like raft_nc_dbl.py:149."""
     image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
     image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
     b = image1.shape[0]
@@ -330,6 +331,7 @@ def raft_forward(sd, image1, image2, iters=12, model="raft_nc_dbl", flow_init=No
     ups = []
     flow_up = None
     for it in range(iters):
+        coords1 = coords1.detach()
         corr = corr_lookup(pyr, coords1)
         flow = coords1 - coords0
         net, mask, delta = update_block(sd, net, inp, corr, flow, with_mask=(model == "raft"))
@@ -344,6 +346,9 @@ def raft_forward(sd, image1, image2, iters=12, model="raft_nc_dbl", flow_init=No
         if trace is not None:
             trace["iters"].append(dict(coords=coords_in, corr=corr, net=net, delta=delta, mask=mask, flow_up=flow_up))
     return coords1 - coords0, flow_up, ups
+
+
+raft_forward = torch.no_grad()(raft_forward_graph)
 
 
 def forward_interpolate(flow):

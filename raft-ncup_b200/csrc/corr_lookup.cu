@@ -181,15 +181,17 @@ corr_lookup_tile_kernel(const float* __restrict__ f1_cl, const float* __restrict
         out[(((size_t)b * K + l * kS * kS + k) * H + qy) * W + qx] = v;
       else if (layout == 1)
         out[((size_t)b * P + qy * W + qx) * ldo + l * lvl_stride + k] = v;
-      else {   // layout 2: exact hi/lo split halves planes (input format of the tcgen05 convolutions)
-        const size_t idx = ((size_t)b * P + qy * W + qx) * ldo + l * lvl_stride + k;
+      else {   // layout 2: exact hi/lo split halves planes (input format of the tcgen05 convolutions), in the resident
+               // channel order of the tensor-core lookup: tap (i, j) -> j*8 + i for i < 8, tap (8, j) -> 72 + j
+        const size_t lvl0 = ((size_t)b * P + qy * W + qx) * ldo + l * lvl_stride;
+        const size_t idx = lvl0 + (i < 8 ? j * 8 + i : 72 + j);
         const float vc = fminf(fmaxf(v, -65504.f), 65504.f);
         const __half hi = __float2half_rn(vc);
         reinterpret_cast<__half*>(out)[idx] = hi;
         out_lo[idx] = __float2half_rn(vc - __half2float(hi));
         if (k < lvl_stride - kS * kS) {          // zero the pad channels of the level (tensor-core consumers read them)
-          reinterpret_cast<__half*>(out)[idx - k + kS * kS + k] = __float2half_rn(0.f);
-          out_lo[idx - k + kS * kS + k] = __float2half_rn(0.f);
+          reinterpret_cast<__half*>(out)[lvl0 + kS * kS + k] = __float2half_rn(0.f);
+          out_lo[lvl0 + kS * kS + k] = __float2half_rn(0.f);
         }
       }
     }

@@ -17,8 +17,14 @@
 // Epilogue (thread = pixel = TMEM lane): two box rows (BW columns each) at a time are read with tcgen05.ld and parked in
 // a thread-private shared-memory row (128-bit stores; dynamic addressing is what shared memory is needed for), the 10
 // lattice values of the pixel's window row are read back, interpolated in x, combined with the previous row in y -> 9
-// outputs (fixed j, i = 0..8) into a staging row, which is written out per level as 16-byte groups of hi/lo split
-// halves (the tcgen05 convolutions' operand format).
+// outputs (fixed j, i = 0..8), which are split into hi/lo halves (the tcgen05 convolutions' operand format) and stored
+// straight into the level's output tile in shared memory; the tile leaves with one TMA store per plane and warp.
+//
+// Output channel order inside a level (kLvlStride = 88 channels; consumed only by convc1, whose weights are permuted to
+// match at pack time — the reference order k = i*9 + j exists only in the seam API, corr_lookup.cu):
+//     tap (i, j), i < 8  ->  j*8 + i          tap (8, j)  ->  72 + j          81..87 = zero pads
+// so the 8 values a thread produces per window row are ONE aligned 16-byte store per plane (conflict-free at the 176-byte
+// pixel pitch) instead of 9 scattered words, and no second pass re-reads / re-packs the level.
 //
 // Tiles whose windows do not fit the fixed boxes (incoherent flow) are flagged and recomputed by the exact CUDA-core
 // kernel (corr_lookup.cu), so the result never depends on the coherence assumption.
@@ -36,13 +42,8 @@ namespace lookup_umma {
 
 using namespace rnc::umma;
 
-// One epilogue warp per TMEM lane group.  (A second warp per lane group splitting the slow window index i was measured
-// on B200 at 0.105 ms vs 0.106 ms per launch: it duplicates the accumulator-row parking, which is most of the work.)
-#ifdef RNC_PROBE_DUPEPI
-constexpr int kEpiWarps = 8;   // probe: a second epilogue warp per lane group repeats the work on aliased buffers
-#else
+// One epilogue warp per TMEM lane group.
 constexpr int kEpiWarps = 4;
-#endif
 constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA + TMEM, then the epilogue warps
 constexpr int kTY = 8, kTX = 16;         // query tile (level-0 pixels)
 constexpr int kD = 256;                  // feature channels
@@ -73,17 +74,19 @@ constexpr int kLvlStride = 88;           // channels per level in the output row
 constexpr int kTiRing = RNC_LOOKUP_TIRING;    // unit records in flight between the producer and its consumers (power of two)
 constexpr int kTiShift = kTiRing == 2 ? 1 : kTiRing == 4 ? 2 : 3;
 constexpr int kSmemA = kKB * kATile;                         // 64 KB
-constexpr int kSmemB = kStages * kBStage;                    // 96 KB
+constexpr int kSmemB = kStages * kBStage;                    // 64 KB
 // Epilogue buffers are pixel-major with 16-byte aligned rows, so a thread moves its data with 128-bit accesses:
 //   scratch [pixel][68]: two box rows (32 words each) of the accumulator; 68 = 4*17 -> the 8 lanes of a quarter warp hit
 //                        8 distinct bank quads
-//   stage   [pixel][84]: the level's 81 taps (+3);       84 = 4*21 -> same property
-#ifndef RNC_LOOKUP_STGSTRIDE
-#define RNC_LOOKUP_STGSTRIDE 84
-#endif
-constexpr int kScrStride = 68, kStgStride = RNC_LOOKUP_STGSTRIDE;
-constexpr int kSmemScratch = 128 * kScrStride * 4;           // 34 KB
-constexpr int kSmemStage = 128 * kStgStride * 4;             // 42 KB
+// scratch [pixel][68] words: two box rows (32 words each); the pixels of the odd tile row of a warp are skewed by 16 words, so
+// that the gather's scalar loads (lane address = 68*pixel + skew + window offset, window offset ~ pixel's x) hit 32 distinct
+// banks: bank = 5*lane + spread (mod 32)
+constexpr int kScrStride = 68, kScrSkew = 16;
+constexpr int kSmemScratch = (128 * kScrStride + kScrSkew) * 4 + 64;   // 34 KB (+ pad to a 128-byte multiple)
+// output tile of one (tile, level) unit: [plane hi | lo][128 px][88 halves], dense = the TMA store's box {88, 16, 2} per warp
+constexpr int kStgPlane = 128 * kLvlStride * 2;              // 22 KB
+constexpr int kSmemStage = 2 * kStgPlane;                    // 44 KB
+static_assert(kSmemScratch % 128 == 0 && (32 * kLvlStride * 2) % 128 == 0, "TMA store sources must be 128-byte aligned");
 #ifdef RNC_PROBE_NOEPI
 constexpr int kSmemTotal = kSmemA + kSmemB + 1024 + 512;     // probe: the epilogue buffers are never touched
 #else
@@ -113,7 +116,7 @@ __device__ __forceinline__ bool window_origin(float cx, float cy, float inv, int
 __device__ __forceinline__ float clamp_coord(float v) { return fminf(fmaxf(v, -1.0e6f), 1.0e6f); }
 
 struct EpiCtx {
-  const Params& p; const TileInfo* ti; float* scratch; float* stage; uint64_t* acc_full; uint64_t* acc_empty;
+  const Params& p; const TileInfo* ti; float* scratch; __half* stage; uint64_t* acc_full; uint64_t* acc_empty;
   uint32_t tmem_base; int b, y0, x0, lg, ml, lane; bool valid; float cx, cy;
 };
 
@@ -128,8 +131,21 @@ template <int BW>
 __device__ __forceinline__ void lookup_level_rows(const EpiCtx& c, int& ch, int l, bool live, int ox, int oy, float ax, float ay) {
   const Params& p = c.p;
   const int cr = chunk_rows(l);
-  float* sc = c.scratch + c.ml * kScrStride;                  // thread-private: two box rows of 32 words
-  float* st = c.stage + c.ml * kStgStride;                    // thread-private: the level's 81 taps
+  float* sc = c.scratch + c.ml * kScrStride + ((c.ml >> 4) & 1) * kScrSkew;   // thread-private: two box rows of 32 words
+  __half* sth = c.stage + c.ml * kLvlStride;                  // this pixel's row of the level's output tile, hi plane
+  __half* stl = sth + 128 * kLvlStride;                       // lo plane
+  // window row j of this pixel is complete: taps (0..7, j) -> one 16-byte store per plane, tap (8, j) -> the tail
+  auto emit = [&](int j, const float (&o)[kS]) {
+    uint32_t hh[4], ll[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) split_pair(o[2 * q], o[2 * q + 1], hh[q], ll[q]);
+    *reinterpret_cast<uint4*>(sth + j * 8) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+    *reinterpret_cast<uint4*>(stl + j * 8) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+    uint32_t h8, l8;
+    split_pair(o[8], 0.f, h8, l8);
+    reinterpret_cast<unsigned short*>(sth)[72 + j] = static_cast<unsigned short>(h8 & 0xffffu);
+    reinterpret_cast<unsigned short*>(stl)[72 + j] = static_cast<unsigned short>(l8 & 0xffffu);
+  };
   const float wx1 = ax * p.scale, wx0 = p.scale - wx1, wy0 = 1.f - ay;   // the 1/sqrt(D) scale rides on the x weights
   // warp-uniform range of box rows that any pixel of this warp (2 tile rows) actually needs
   const int row_lo = __reduce_min_sync(0xffffffffu, live ? oy : 0x7fffffff);
@@ -157,12 +173,16 @@ __device__ __forceinline__ void lookup_level_rows(const EpiCtx& c, int& ch, int 
       for (int i = 0; i < kS; ++i) h1[i] = wx0 * g1[i] + wx1 * g1[i + 1];
     }
     if (live && cidx >= 1 && cidx < kG) {
+      float o[kS];
 #pragma unroll
-      for (int i = 0; i < kS; ++i) st[i * kS + cidx - 1] = wy0 * hprev[i] + ay * h0[i];
+      for (int i = 0; i < kS; ++i) o[i] = wy0 * hprev[i] + ay * h0[i];
+      emit(cidx - 1, o);
     }
     if (TWO && live && cidx >= 0 && cidx < kG - 1) {
+      float o[kS];
 #pragma unroll
-      for (int i = 0; i < kS; ++i) st[i * kS + cidx] = wy0 * h0[i] + ay * h1[i];
+      for (int i = 0; i < kS; ++i) o[i] = wy0 * h0[i] + ay * h1[i];
+      emit(cidx, o);
     }
 #pragma unroll
     for (int i = 0; i < kS; ++i) hprev[i] = TWO ? h1[i] : h0[i];
@@ -208,12 +228,12 @@ __device__ __forceinline__ void lookup_level_rows(const EpiCtx& c, int& ch, int 
   }
 }
 
-// Epilogue of one warp (thread = pixel = TMEM lane) for one unit = (tile, level l): rows, then write-out.
-__device__ __forceinline__ void lookup_epilogue(const EpiCtx& c, int& ch, int l) {
+// Epilogue of one warp (thread = pixel = TMEM lane) for one unit = (tile, level l): rows into the output tile, then one TMA
+// store per plane of the warp's 2 x 16 pixels (the TMA unit clips pixels beyond the image).
+__device__ __forceinline__ void lookup_epilogue(const EpiCtx& c, int& ch, int l, const CUtensorMap* map_hi, const CUtensorMap* map_lo) {
   const Params& p = c.p;
-  const int HW = p.H * p.W;
-  float* st = c.stage + c.ml * kStgStride;
-  const int qy = c.y0 + (c.ml >> 4), qx = c.x0 + (c.ml & 15);
+  __half* sth = c.stage + c.ml * kLvlStride;
+  __half* stl = sth + 128 * kLvlStride;
   const float inv = 1.f / static_cast<float>(1 << l);
   const float sx = c.cx * inv, sy = c.cy * inv;
   const float ax = sx - floorf(sx), ay = sy - floorf(sy);
@@ -221,46 +241,35 @@ __device__ __forceinline__ void lookup_epilogue(const EpiCtx& c, int& ch, int l)
   const bool empty = !window_origin(c.cx, c.cy, inv, p.H >> l, p.W >> l, ix0, iy0);
   const int ox = ix0 - c.ti->bx0, oy = iy0 - c.ti->by0;
   const bool live = c.valid && !empty;
-  if (c.valid && empty) {
-    for (int k = 0; k < kS * kS; ++k) st[k] = 0.f;
+  // the previous unit's TMA stores have finished READING this warp's rows of the output tile
+  if (c.lane == 0) bulk_wait_read0();
+  __syncwarp();
+#ifndef RNC_PROBE_NOEPI
+  if (!live) {                                 // window fully outside the level image (or pixel outside the frame): zeros
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int q = 0; q < 10; ++q) {
+      *reinterpret_cast<uint4*>(sth + q * 8) = z;
+      *reinterpret_cast<uint4*>(stl + q * 8) = z;
+    }
+    reinterpret_cast<unsigned short*>(sth)[80] = 0;
+    reinterpret_cast<unsigned short*>(stl)[80] = 0;
   }
+#endif
   if (l == 0) lookup_level_rows<box_w(0)>(c, ch, l, live, ox, oy, ax, ay);
   else if (l == 1) lookup_level_rows<box_w(1)>(c, ch, l, live, ox, oy, ax, ay);
   else lookup_level_rows<box_w(2)>(c, ch, l, live, ox, oy, ax, ay);
   static_assert(box_w(2) == box_w(3), "levels 2 and 3 share the row code");
-  // ---- The level occupies kLvlStride (= 88, a multiple of 8) channels of the output row: 81 taps + 7 zero pads, so every
-  // group of 8 channels is one aligned 16-byte store per plane.  Two groups per step (independent chains).
-#ifdef RNC_PROBE_NOEPI
-  if (false) {
-#else
-  if (qy < p.H && qx < p.W) {
-#endif
-    const size_t base = (static_cast<size_t>(c.b) * HW + qy * p.W + qx) * p.ldo + l * kLvlStride;
-    auto emit = [&](const float (&v)[8], int gq) {
-      uint32_t hh[4], ll[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) split_pair(v[2 * j], v[2 * j + 1], hh[j], ll[j]);
-      *reinterpret_cast<uint4*>(p.out_hi + base + gq * 8) = *reinterpret_cast<uint4*>(hh);
-      *reinterpret_cast<uint4*>(p.out_lo + base + gq * 8) = *reinterpret_cast<uint4*>(ll);
-    };
-#pragma unroll 1
-    for (int gq = 0; gq < 10; gq += 2) {
-      float va[8], vb[8];
-      if (kStgStride % 4 == 0) {
-        const float4 a0 = *reinterpret_cast<const float4*>(st + gq * 8), a1 = *reinterpret_cast<const float4*>(st + gq * 8 + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(st + gq * 8 + 8), b1 = *reinterpret_cast<const float4*>(st + gq * 8 + 12);
-        va[0] = a0.x; va[1] = a0.y; va[2] = a0.z; va[3] = a0.w; va[4] = a1.x; va[5] = a1.y; va[6] = a1.z; va[7] = a1.w;
-        vb[0] = b0.x; vb[1] = b0.y; vb[2] = b0.z; vb[3] = b0.w; vb[4] = b1.x; vb[5] = b1.y; vb[6] = b1.z; vb[7] = b1.w;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { va[j] = st[gq * 8 + j]; vb[j] = st[gq * 8 + 8 + j]; }
-      }
-      emit(va, gq);
-      emit(vb, gq + 1);
-    }
-    const float vt[8] = {st[80], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // tap 80 + the 7 zero pads
-    emit(vt, 10);
+#ifndef RNC_PROBE_NOEPI
+  fence_proxy_async();                         // this thread's shared-memory writes are visible to the TMA unit
+  __syncwarp();
+  if (c.lane == 0) {
+    const __half* src = c.stage + c.lg * 32 * kLvlStride;
+    tma_store_4d(map_hi, src, l * kLvlStride, c.x0, c.y0 + 2 * c.lg, c.b);
+    tma_store_4d(map_lo, src + 128 * kLvlStride, l * kLvlStride, c.x0, c.y0 + 2 * c.lg, c.b);
+    bulk_commit();
   }
+#endif
 }
 
 // Work units.  A unit is (tile, level): 3, 2, 1, 1 accumulator chunks.  Units are listed level-major (all level-0 units
@@ -288,13 +297,14 @@ __device__ __forceinline__ int unit_at(int k, int nunits, int tile_major) {
 __global__ void __launch_bounds__(kThreads, 1)
 corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_constant__ CUtensorMap mL0,
                         const __grid_constant__ CUtensorMap mL1, const __grid_constant__ CUtensorMap mL2,
-                        const __grid_constant__ CUtensorMap mL3, const Params p) {
+                        const __grid_constant__ CUtensorMap mL3, const __grid_constant__ CUtensorMap mOutHi,
+                        const __grid_constant__ CUtensorMap mOutLo, const Params p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned, stays in the shared window
   unsigned char* sA = smem;
   unsigned char* sB = smem + kSmemA;
   float* scratch = reinterpret_cast<float*>(smem + kSmemA + kSmemB);
-  float* stage = reinterpret_cast<float*>(smem + kSmemA + kSmemB + kSmemScratch);
+  __half* stage = reinterpret_cast<__half*>(smem + kSmemA + kSmemB + kSmemScratch);
   unsigned char* tail = smem + kSmemTotal - 1024 - 512;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);       // [kKB]
   uint64_t* a_empty = a_full + kKB;                           // [kKB]
@@ -538,6 +548,13 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
     };
     float cx = 0.f, cy = 0.f, ncx = 0.f, ncy = 0.f;
     bool valid = false, nvalid = false;
+#ifndef RNC_PROBE_NOEPI
+    {                                          // the 7 pad channels of this pixel's output rows stay zero for the whole kernel
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(stage + ml * kLvlStride + 80) = z;
+      *reinterpret_cast<uint4*>(stage + (128 + ml) * kLvlStride + 80) = z;
+    }
+#endif
     int unit = unit_at(0, nunits, tm);
     if (unit >= 0) load_coord(unit % ntiles, ncx, ncy, nvalid);
     int ch = 0, n = 0;
@@ -553,19 +570,14 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
       const int slot = n & (kTiRing - 1);
       mbar_wait(&ti_full[slot], (n >> kTiShift) & 1);
       if (!ti[slot].overflow) {
-#ifdef RNC_PROBE_DUPEPI
-        float* scr = warp >= 6 ? reinterpret_cast<float*>(sA) : scratch;
-        float* stg = warp >= 6 ? reinterpret_cast<float*>(sA + kSmemScratch) : stage;
-        EpiCtx c{p, &ti[slot], scr, stg, acc_full, acc_empty, tmem_base, b, y0, x0, lg, ml, lane, valid, cx, cy};
-#else
         EpiCtx c{p, &ti[slot], scratch, stage, acc_full, acc_empty, tmem_base, b, y0, x0, lg, ml, lane, valid, cx, cy};
-#endif
-        lookup_epilogue(c, ch, l);
+        lookup_epilogue(c, ch, l, &mOutHi, &mOutLo);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&ti_empty[slot]);
       ++n;
     }
+    if (lane == 0) bulk_wait_all0();           // the output tile must outlive its TMA stores
   }
 
   tcgen05_fence_before();
@@ -633,7 +645,7 @@ extern "C" int rnc_corr_lookup_umma_fwd(const void* f1h_cl, const void* f2h_pyr,
   if (D != kD || levels != kLevels || radius != kR) return RNC_ERR_UNSUPPORTED;
   if ((H >> (levels - 1)) < 1 || (W >> (levels - 1)) < 1 || ldo < levels * kLvlStride || (ldo & 7) || lvl_stride != kLvlStride) return RNC_ERR_BAD_SHAPE;
   if (!f1h_cl || !f2h_pyr || !f1_cl || !f2_pyr || !coords || !out_hi || !out_lo || !workspace) return RNC_ERR_BAD_POINTER;
-  if (!aligned16(f1h_cl) || !aligned16(f2h_pyr) || !aligned16(workspace)) return RNC_ERR_BAD_POINTER;
+  if (!aligned16(f1h_cl) || !aligned16(f2h_pyr) || !aligned16(workspace) || !aligned16(out_hi) || !aligned16(out_lo)) return RNC_ERR_BAD_POINTER;
   if (workspace_bytes < rnc_corr_lookup_umma_workspace_bytes(B, H, W)) return RNC_ERR_WORKSPACE;
   if (!encode_fn()) return RNC_ERR_UNSUPPORTED;
 
@@ -651,8 +663,11 @@ extern "C" int rnc_corr_lookup_umma_fwd(const void* f1h_cl, const void* f2h_pyr,
     p.tile_major = env != nullptr && env[0] == 't';
   }
 
-  CUtensorMap maps[5];
+  CUtensorMap maps[7];
   bool ok = make_act_map(&maps[0], f1h_cl, kD, kD, B, H, W, kTX, kTY);
+  // output planes [B][H][W][ldo] halves: un-swizzled store boxes of one level (88 channels) x 16 x 2 pixels
+  ok = ok && make_plain_map(&maps[5], out_hi, ldo, ldo, B, H, W, kLvlStride, kTX, 2);
+  ok = ok && make_plain_map(&maps[6], out_lo, ldo, ldo, B, H, W, kLvlStride, kTX, 2);
   size_t off = 0;
   for (int l = 0; l < kLevels; ++l) {
     const int Hl = H >> l, Wl = W >> l;
@@ -666,7 +681,7 @@ extern "C" int rnc_corr_lookup_umma_fwd(const void* f1h_cl, const void* f2h_pyr,
   const int ntiles = B * p.tiles_x * p.tiles_y;
   const int grid = ntiles * kLevels < sm_count() ? ntiles * kLevels : sm_count();   // persistent: one CTA per SM
   cudaError_t e = launch_pdl(corr_lookup_umma_kernel, dim3(grid), dim3(kThreads), kSmemTotal, as_stream(stream), maps[0], maps[1], maps[2],
-                             maps[3], maps[4], p);
+                             maps[3], maps[4], maps[5], maps[6], p);
   if (e != cudaSuccess) { g_last_cuda_error = static_cast<int>(e); return RNC_ERR_CUDA; }
   if (int st = after_launch()) return st;
   // exact recomputation of the tiles the fixed boxes could not cover

@@ -16,11 +16,21 @@ CORR_LS = 88           # channels reserved per pyramid level in the resident cor
 CORR_LD = 4 * CORR_LS  # 352: row pitch of the corr halves planes; convc1 still needs only 6 K-blocks of 64
 
 
-def expand_corr_weight(weight):
-    """convc1 weight [Cout, 324, 1, 1] -> [Cout, 352, 1, 1] in the padded per-level layout (zeros at the pads)."""
-    w = torch.zeros(weight.shape[0], CORR_LD, 1, 1, dtype=torch.float32, device=weight.device)
+def corr_resident_index(device=None):
+    """Reference channel k = l*81 + i*9 + j (corr.py:41-44)  ->  its position in the resident corr row of the tensor-core path:
+    l*88 + (j*8 + i if i < 8 else 72 + j) — a pixel's 8 values of one window row are one aligned 16-byte group (rnc.h)."""
+    idx = torch.empty(CORR_CH, dtype=torch.long)
     for lvl in range(4):
-        w[:, lvl * CORR_LS: lvl * CORR_LS + 81] = weight.detach().float()[:, lvl * 81:(lvl + 1) * 81]
+        for i in range(9):
+            for j in range(9):
+                idx[lvl * 81 + i * 9 + j] = lvl * CORR_LS + (j * 8 + i if i < 8 else 72 + j)
+    return idx.to(device) if device is not None else idx
+
+
+def expand_corr_weight(weight):
+    """convc1 weight [Cout, 324, 1, 1] -> [Cout, 352, 1, 1] in the resident channel order (zeros at the pads)."""
+    w = torch.zeros(weight.shape[0], CORR_LD, 1, 1, dtype=torch.float32, device=weight.device)
+    w[:, corr_resident_index(weight.device)] = weight.detach().float()
     return w
 GIN_LD = 136           # 2 + 128 (+2 zero) channels of the weights-net input, pitch multiple of 16 B
 
@@ -346,9 +356,15 @@ class UmmaEngine(Engine):
         B, _, H, W = corr_nchw.shape
         tmp = torch.empty(B * H * W, CORR_CH, dtype=torch.float32, device=corr_nchw.device)
         native.check(self.L.rnc_nchw_to_cl(_ptr(corr_nchw), B, CORR_CH, H, W, _ptr(tmp), CORR_CH, 0, _stream()), "nchw_to_cl(corr)")
-        for lvl in range(4):     # level l -> channels [l*88, l*88+81); the pads stay zero
-            native.check(self.L.rnc_f32_to_split(C.c_void_p(tmp.data_ptr() + 4 * 81 * lvl), CORR_CH, 81, B * H * W, _ptr(ws.corr.hi),
-                                                 _ptr(ws.corr.lo), CORR_LD, lvl * CORR_LS, _stream()), "f32_to_split(corr)")
+        res = torch.zeros(B * H * W, CORR_LD, dtype=torch.float32, device=corr_nchw.device)     # layout plumbing: resident order
+        res[:, corr_resident_index(res.device)] = tmp
+        native.check(self.L.rnc_f32_to_split(_ptr(res), CORR_LD, CORR_LD, B * H * W, _ptr(ws.corr.hi), _ptr(ws.corr.lo), CORR_LD, 0,
+                                             _stream()), "f32_to_split(corr)")
+
+    def corr_nchw(self, ws):
+        """The resident corr row back in the reference's layout [B, 324, H8, W8] (tests / debugging)."""
+        v = (ws.corr.hi.float() + ws.corr.lo.float())[:, corr_resident_index(ws.corr.hi.device)]
+        return v.view(ws.B, ws.H8, ws.W8, CORR_CH).permute(0, 3, 1, 2).contiguous()
 
     def net_nchw(self, ws):
         out = torch.empty(ws.B, 128, ws.H8, ws.W8, dtype=torch.float32, device=ws.h.device)

@@ -52,3 +52,52 @@ def readFlowKITTI(filename):
     import cv2
     raw = cv2.imread(filename, cv2.IMREAD_ANYDEPTH | cv2.IMREAD_COLOR)[:, :, ::-1].astype(np.float32)
     return (raw[:, :, :2] - 2 ** 15) / 64.0, raw[:, :, 2]
+
+
+def readPFM(filename):
+    """frame_utils.py:33-68 — PFM ('PF' colour / 'Pf' grey), scale < 0 = little endian; rows are stored bottom-up."""
+    import re
+    with open(filename, "rb") as f:
+        header = f.readline().rstrip()
+        if header == b"PF":
+            color = True
+        elif header == b"Pf":
+            color = False
+        else:
+            raise Exception("Not a PFM file.")
+        dim = re.match(rb"^(\d+)\s(\d+)\s$", f.readline())
+        if not dim:
+            raise Exception("Malformed PFM header.")
+        width, height = int(dim.group(1)), int(dim.group(2))
+        scale = float(f.readline().rstrip())
+        endian = "<" if scale < 0 else ">"
+        data = np.frombuffer(f.read(), dtype=endian + "f4")
+    shape = (height, width, 3) if color else (height, width)
+    return np.flipud(np.reshape(data, shape))
+
+
+def readDispKITTI(filename):
+    """frame_utils.py:109-113 — 16-bit disparity PNG -> (flow [H,W,2] with u = -disp, valid)."""
+    import cv2
+    disp = cv2.imread(filename, cv2.IMREAD_ANYDEPTH) / 256.0
+    valid = disp > 0.0
+    return np.stack([-disp, np.zeros_like(disp)], -1), valid
+
+
+def read_gen(file_name, pil=False):
+    """frame_utils.py:123-142 — dispatch on the file extension, as the datasets do."""
+    from os.path import splitext
+    ext = splitext(file_name)[-1]
+    if ext in (".png", ".jpeg", ".ppm", ".jpg", ".webp"):
+        from PIL import Image
+        return Image.open(file_name)
+    if ext in (".bin", ".raw"):
+        return np.load(file_name)
+    if ext == ".flo":
+        return readFlow(file_name).astype(np.float32)
+    if ext == ".pfm":
+        flow = readPFM(file_name).astype(np.float32)
+        return flow if flow.ndim == 2 else flow[:, :, :-1]
+    if ext == ".npz":
+        return np.load(file_name)["optical_flow"].astype(np.float32).transpose(1, 2, 0)
+    return []

@@ -272,8 +272,9 @@ def resident_lookup(f1, f2, coords, lookup_mode):
     torch.cuda.synchronize()
     out = (ws.corr.hi.float() + ws.corr.lo.float()).view(-1, 4, 88)        # padded per-level layout: 81 taps + 7 zero pads
     assert (out[:, :, 81:] == 0).all() and (ws.corr.lo.view(-1, 4, 88)[:, :, 81:] == 0).all()
+    assert (out[:, :, :81] != 7.0).all()                                    # every tap of every pixel was written
     flags = ws.lookup_flags.cpu() if lookup_mode == "umma" else None
-    return out[:, :, :81].reshape(B, H, W, 324).permute(0, 3, 1, 2).cpu(), flags
+    return eng.corr_nchw(ws).cpu(), flags                                   # resident channel order -> reference order
 
 
 def fp16_tol(f1, f2):
