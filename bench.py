@@ -1,8 +1,13 @@
 """bench.py — image-pairs/s of the RAFT-NCUP hot path at 1024x436, 32 iterations (BASELINE.json metric), with the
 corr-lookup kernel's HBM roofline and the CPU baseline beside it.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference|reference_gpu] [--model raft_nc_dbl|raft]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+--impl reference      the UNMODIFIED reference (baseline/_ref, installed by baseline/install_reference.sh) on the host CPU cores
+--impl reference_gpu  the same reference modules in eager PyTorch on the GPU, TF32 off ("the bar"); the native
+                      arm runs this leg in a subprocess (the reference's module names clash with the drop-in's) and reports it
+                      as `gpu_eager_baseline`
 
 A "step" = one RAFT.forward over one batch of synthetic pairs (BASELINE configs[2]: batch 8 per GPU, 1024x436 padded to
 440, 32 iterations, model raft_nc_dbl = full path incl. the NCUP upsampler; configs[1]'s corr-lookup kernel is timed
@@ -19,15 +24,30 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (ROOT, os.path.join(ROOT, "raft-ncup_b200"), os.path.join(ROOT, "tests")):
-    if _p not in sys.path:
-        sys.path.insert(0, _p)
+PKG = os.path.join(ROOT, "raft-ncup_b200")
+REF_CORE = os.path.join(ROOT, "baseline", "_ref", "core")        # pip-installed copy of the unmodified reference (git-ignored)
 
 import torch  # noqa: E402
+
+
+def use_product_path():
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+
+
+def use_reference_path():
+    """The reference is a directory of scripts that does `sys.path.append('core')` (evaluate.py:2): same here."""
+    if not os.path.isdir(REF_CORE):
+        return False
+    if REF_CORE not in sys.path:
+        sys.path.insert(0, REF_CORE)
+    return True
 
 H_IMG, W_IMG, ITERS, BATCH = 436, 1024, 32, 8
 K2_BYTES_PER_PAIR_ITER = 25_891_840      # SURVEY.md §8(d): fmap1 + coords + out + fmap2 pyramid, fp32
 K4_BYTES_PER_PAIR_CALL = 3_886_080       # SURVEY.md §8(d): flow_lr + conf read, 2x64xP fp32 written
+K5_BYTES_PER_PAIR_CALL = 19_880_960      # SURVEY.md §8(d): mask 16,220,160 + flow 56,320 + out 3,604,480
 # same formula at the storage width the tensor-core lookup uses: fp16 fmap1/fmap2 pyramid, fp32 coords, 2 x fp16 outputs
 K2_STORAGE_BYTES_PER_PAIR_ITER = 2 * 7040 * 256 + 8 * 7040 + 4 * 7040 * 324 + 2 * 256 * 9280
 
@@ -55,8 +75,30 @@ def synth_frames(b, seed):
     g = torch.Generator().manual_seed(seed)
     im1 = torch.rand(b, 3, H_IMG, W_IMG, generator=g) * 255
     im2 = torch.rand(b, 3, H_IMG, W_IMG, generator=g) * 255
-    from utils.utils import InputPadder
-    return InputPadder(im1.shape, "sintel").pad(im1, im2)           # 436 -> 440 (evaluate.py:125-126)
+    ph = (8 - H_IMG % 8) % 8                                        # InputPadder 'sintel' (utils.py:12-15): 436 -> 440, split evenly
+    return [torch.nn.functional.pad(x, [0, 0, ph // 2, ph - ph // 2], mode="replicate") for x in (im1, im2)]
+
+
+def ref_args(dataset="sintel"):
+    """The flag values every reference script ships (eval_raft_nc_sintel.sh:12-34)."""
+    return argparse.Namespace(
+        small=False, mixed_precision=False, load_pretrained=None, freeze_raft=False, dataset=dataset, align_corners=True,
+        final_upsampling="NConvUpsampler", final_upsampling_scale=4, final_upsampling_use_data_for_guidance=True,
+        final_upsampling_channels_to_batch=True, final_upsampling_use_residuals=False, final_upsampling_est_on_high_res=False,
+        interp_net="NConvUNet", interp_net_channels_multiplier=2, interp_net_num_downsampling=1,
+        interp_net_data_pooling="conf_based", interp_net_encoder_filter_sz=5, interp_net_decoder_filter_sz=3,
+        interp_net_out_filter_sz=1, interp_net_shared_encoder=True, interp_net_use_double_conv=False, interp_net_use_bias=False,
+        weights_est_net="Simple", weights_est_net_num_ch=[64, 32], weights_est_net_filter_sz=[3, 3, 1],
+        weights_est_net_dilation=[1, 1, 1])
+
+
+def reference_model(name):
+    """RAFT(args) of the unmodified reference (baseline/_ref/core/raft_nc_dbl.py:26 / raft.py:24), seed 1234 (train.py:345)."""
+    import importlib
+    import warnings
+    warnings.filterwarnings("ignore")
+    torch.manual_seed(1234)
+    return importlib.import_module(name).RAFT(ref_args()).eval()
 
 
 class ClockSampler:
@@ -107,37 +149,101 @@ def host_cores():
     return n
 
 
-def cpu_oracle_pairs_per_s(steps, warmup):
-    """The reference's algorithm on the host cores: oracle/raft_oracle.py (a torch-CPU restatement pinned to the reference
-    by tests/golden).  One step = ONE pair at the full 1024x436 / 32-iteration shape (bounded sample of the 8-pair batch)."""
-    from conftest import build_model
-    from oracle import raft_oracle as orc
+def cpu_reference_pairs_per_s(steps, warmup, model_name="raft_nc_dbl"):
+    """The reference's own CPU path on the host cores: RAFT(args).eval() from baseline/_ref under torch.no_grad(), fp32, all
+    the cores the cgroup allows.  One step = ONE pair at the full 1024x436 / 32-iteration shape (a bounded sample of the 8-pair
+    batch: ~7 s).  Falls back to the oracle port (pinned to the reference by tests/golden) when baseline/_ref is absent.
+    Returns (pairs/s, s/step, kind)."""
     torch.set_num_threads(host_cores())
-    sd = {k: v.detach() for k, v in build_model("raft_nc_dbl").state_dict().items()}
     p1, p2 = synth_frames(1, 7)
+    if use_reference_path():
+        model = reference_model(model_name)
+        kind = "reference"
+
+        def step():
+            with torch.no_grad():
+                return model(p1, p2, iters=ITERS, test_mode=True)     # upsamples every iteration (raft_nc_dbl.py:161)
+    else:
+        use_product_path()
+        from oracle import raft_oracle as orc
+        from rnc.synth import build_model
+        sd = {k: v.detach() for k, v in build_model(model_name).state_dict().items()}
+        kind = "port"
+
+        def step():
+            return orc.raft_forward(sd, p1, p2, iters=ITERS, model=model_name)
     for _ in range(warmup):
-        orc.raft_forward(sd, p1, p2, iters=ITERS, model="raft_nc_dbl")
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        orc.raft_forward(sd, p1, p2, iters=ITERS, model="raft_nc_dbl")      # upsamples every iteration, like raft_nc_dbl.py:161
+        step()
     dt = (time.perf_counter() - t0) / steps
-    return 1.0 / dt, dt
+    return 1.0 / dt, dt, kind
+
+
+CPU_SAMPLE = "1 pair per step at 1024x436 (pad 440), 32 iters, NCUP upsampling every iteration as the reference does"
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    steps, warmup = args.steps, args.warmup
-    v, dt = cpu_oracle_pairs_per_s(steps, min(warmup, 1))
+    steps, warmup = args.steps, min(args.warmup, 1)
+    v, dt, kind = cpu_reference_pairs_per_s(steps, warmup, args.model)
     cores = torch.get_num_threads()
-    sample = "1 pair per step at 1024x436 (pad 440), 32 iters, NCUP upsampling every iteration as the reference does"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2/3: 1024x436 (pad 440), 32 iters, raft_nc_dbl full path incl. NCUP", "device": "host CPU"},
-        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": f"cfg2/3: 1024x436 (pad 440), 32 iters, {args.model} full path incl. the upsampler, B=1 per step "
+                               "(bounded sample of the B=8 batch)", "device": "host CPU",
+                   "implementation": "unmodified reference modules from baseline/_ref" if kind == "reference" else "oracle port"},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": CPU_SAMPLE},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_reference_gpu(args):
+    """SURVEY.md §0.1 / BASELINE.md §3.5: the reference's eager PyTorch path on the same B200 (cuBLAS bmm volume + grid_sample
+    + cuDNN convolutions), TF32 off so that it computes what its CPU path computes.  CUDA events, warm-up, one JSON line."""
+    if not use_reference_path() or not torch.cuda.is_available():
+        print(json.dumps({"impl": "reference_gpu", "unavailable": "baseline/_ref or GPU missing"}))
+        return
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda", 0)
+    model = reference_model(args.model).to(dev)
+    p1, p2 = synth_frames(args.batch, 7)
+    d1, d2 = p1.to(dev), p2.to(dev)
+    times = []
+    with torch.no_grad():
+        for i in range(max(1, args.warmup) + args.steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            lo, up = model(d1, d2, iters=ITERS, test_mode=True)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= max(1, args.warmup):
+                times.append(e0.elapsed_time(e1))
+    ms = sum(times) / len(times)
+    print(json.dumps({"impl": "reference_gpu", "metric": METRIC, "value": args.batch / (ms * 1e-3), "unit": "pairs/s",
+                      "ms_per_step": ms, "steps": args.steps, "batch": args.batch, "model": args.model, "dtype": "f32",
+                      "tf32": False, "checksum_flow_up_abs_mean": float(up.abs().mean()),
+                      "note": "unmodified reference modules (baseline/_ref) .cuda(), eager PyTorch, cudnn/matmul TF32 disabled, "
+                              "inputs resident, CUDA events"}))
+
+
+def gpu_eager_baseline(args):
+    """Run the reference_gpu leg in a fresh process (module names `raft_nc_dbl`, `update`, `corr`, ... clash with the drop-in)."""
+    if not os.path.isdir(REF_CORE):
+        return {"unavailable": "baseline/_ref not installed (run baseline/install_reference.sh)"}
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference_gpu", "--steps", "2", "--warmup", "1",
+           "--batch", str(args.batch), "--model", args.model]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=900,
+                             env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+        line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+        return json.loads(line)
+    except Exception as e:     # noqa: BLE001 — the baseline leg must never take the bench down
+        return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
 def mean_ms(pairs):
@@ -146,8 +252,9 @@ def mean_ms(pairs):
 
 def run_native(args, rank, world, local_rank):
     import torch.distributed as dist
-    from conftest import build_model
+    use_product_path()
     from rnc import native
+    from rnc.synth import build_model, motion_boundary_flow_init
     assert torch.cuda.is_available(), "bench.py --impl native needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -234,7 +341,7 @@ def run_native(args, rank, world, local_rank):
     # the lookup kernel alone (in the timed region convf1 runs underneath it on a side stream): 32 back-to-back launches
     iso_ms = None
     if hasattr(eng, "lookup_resident"):
-        ws = next(iter(eng._ws.values()))
+        ws = next(w for k, w in eng._ws.items() if k[0] == eng.mode and w.B == args.batch)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -243,6 +350,59 @@ def run_native(args, rank, world, local_rank):
         e1.record()
         torch.cuda.synchronize()
         iso_ms = e0.elapsed_time(e1) / ITERS
+    # (tile, level) units of the LAST lookup launch that the fixed boxes could not cover (recomputed by the exact kernel),
+    # and the same kernel on the motion-boundary stimulus (flow discontinuities of 24 px at 1/8 resolution)
+    fb_units = mb_ms = mb_units = None
+    if hasattr(eng, "lookup_resident") and getattr(eng, "lookup_mode", "") == "umma":
+        fb_units = int((ws.lookup_flags != 0).sum().item())
+        keep = ws.coords1.clone()
+        ws.coords1.add_(motion_boundary_flow_init(args.batch, ws.H8, ws.W8).to(dev))
+        for _ in range(2):
+            eng.lookup_resident(ws)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(ITERS):
+            eng.lookup_resident(ws)
+        e1.record()
+        torch.cuda.synchronize()
+        mb_ms = e0.elapsed_time(e1) / ITERS
+        mb_units = int((ws.lookup_flags != 0).sum().item())
+        ws.coords1.copy_(keep)
+    # K5 (convex upsampler of model `raft`) alone on cfg-2/3 shaped buffers: 20 launches
+    k5_ms = None
+    if rank == 0:
+        mk = torch.randn(args.batch * 55 * 128, 576, device=dev)
+        fl = torch.randn(args.batch, 2, 55, 128, device=dev)
+        dims = type("D", (), {"B": args.batch, "H8": 55, "W8": 128})()
+        for _ in range(3):
+            eng.convex_upsample(dims, fl, mk, 576)
+        flush.zero_()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            eng.convex_upsample(dims, fl, mk, 576)
+        e1.record()
+        torch.cuda.synchronize()
+        k5_ms = e0.elapsed_time(e1) / 20
+        del mk, fl
+    # single pair latency (the reference's evaluate.py usage: B = 1)
+    b1_ms = None
+    if rank == 0:
+        with torch.no_grad():
+            for _ in range(2):
+                model(d1[:1], d2[:1], iters=ITERS, test_mode=True)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                model(d1[:1], d2[:1], iters=ITERS, test_mode=True)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+        b1_ms = statistics.median(ts)
     clocks = sampler.stop() if rank == 0 else None
 
     pairs = world * args.batch * args.steps
@@ -278,6 +438,13 @@ def run_native(args, rank, world, local_rank):
                                                "width actually used (fp16 features, 4 B hi/lo outputs) one launch moves "
                                                f"{K2_STORAGE_BYTES_PER_PAIR_ITER * args.batch} B",
                      "avg_launch_ms": k2_ms, "launches_timed": len(prof.get("corr_lookup", [])),
+                     "storage_width": {"bytes_per_launch": K2_STORAGE_BYTES_PER_PAIR_ITER * args.batch,
+                                       "frac": (K2_STORAGE_BYTES_PER_PAIR_ITER * args.batch / (k2_ms * 1e-3) / 1e9 / peak) if k2_ms else None},
+                     "fallback_units_per_launch": fb_units, "units_per_launch": args.batch * 56 * 4,
+                     "motion_boundary": {"avg_launch_ms": mb_ms, "fallback_units_per_launch": mb_units,
+                                         "frac": (k2_bytes / (mb_ms * 1e-3) / 1e9 / peak) if mb_ms else None,
+                                         "note": "same launch with a 24 px (1/8-res) flow discontinuity added to coords1: boundary "
+                                                 "tiles go through the exact CUDA-core kernel"},
                      "isolated": {"avg_launch_ms": iso_ms, "achieved": (k2_bytes / (iso_ms * 1e-3) / 1e9) if iso_ms else None,
                                   "frac": (k2_bytes / (iso_ms * 1e-3) / 1e9 / peak) if iso_ms else None,
                                   "note": "same kernel, 32 back-to-back launches outside the timed region (warm L2, no "
@@ -285,14 +452,37 @@ def run_native(args, rank, world, local_rank):
         "roofline_ncup": {"kernel": "ncup_fused_kernel (K4)", "bound": "hbm", "achieved": k4_gbs, "peak": peak, "unit": "GB/s",
                           "frac": k4_gbs / peak, "avg_launch_ms": k4_ms,
                           "algorithmic_bytes_per_launch": K4_BYTES_PER_PAIR_CALL * args.batch},
+        "roofline_convex": {"kernel": "convex_upsample_kernel (K5, model raft)", "bound": "hbm",
+                            "achieved": (K5_BYTES_PER_PAIR_CALL * args.batch / (k5_ms * 1e-3) / 1e9) if k5_ms else None, "peak": peak,
+                            "unit": "GB/s", "frac": (K5_BYTES_PER_PAIR_CALL * args.batch / (k5_ms * 1e-3) / 1e9 / peak) if k5_ms else None,
+                            "avg_launch_ms": k5_ms, "algorithmic_bytes_per_launch": K5_BYTES_PER_PAIR_CALL * args.batch,
+                            "note": "20 back-to-back launches on cfg-2/3 shaped buffers (mask 130 MB > L2)"},
         "update_block": {"avg_iter_ms": ub_ms, "tflops_fp32_equiv": ub_tflops, "flop_per_pair_iter": 37.7e9},
+        "latency_b1_ms": b1_ms,
     }
     if world == 1 and not args.no_cpu_baseline:
-        v, dt = cpu_oracle_pairs_per_s(1, 0)
-        line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": "1 pair (of the 8-pair batch) at 1024x436/32 iters through oracle/raft_oracle.py, "
-                                          f"1 run, {dt:.1f} s"}
+        del model, d1, d2, stage, flush
+        torch.cuda.empty_cache()
+        line["gpu_eager_baseline"] = gpu_eager_baseline(args)
+        ge = line["gpu_eager_baseline"].get("value")
+        if ge:
+            line["gpu_eager_baseline"]["speedup_value_over_eager"] = value / ge
+        line["cpu_baseline"] = cpu_baseline_subprocess(args)
     print(json.dumps(line))
+
+
+def cpu_baseline_subprocess(args):
+    """The reference's CPU path, one bounded step, in a fresh process (same module-name clash as the GPU leg)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0", "--model", args.model]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600,
+                             env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+        ref = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+        cb = ref["cpu_baseline"]
+        cb["sample"] += f"; 1 run, {ref['ms_per_step'] / 1e3:.1f} s"
+        return cb
+    except Exception as e:     # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
 def main():
@@ -300,7 +490,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "reference_gpu"])
     ap.add_argument("--model", default="raft_nc_dbl", choices=["raft_nc_dbl", "raft"])
     ap.add_argument("--batch", type=int, default=BATCH, help="pairs per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -310,6 +500,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.impl == "reference_gpu":
+        if rank == 0:
+            run_reference_gpu(args)
         return
     if world > 1:
         import torch.distributed as dist

@@ -450,8 +450,9 @@ class Engine:
     # ------------------------------------------------------------------ upsamplers
     def convex_upsample(self, ws, flow_low, mask_cl, ldm):
         out = torch.empty(ws.B, 2, 8 * ws.H8, 8 * ws.W8, dtype=torch.float32, device=flow_low.device)
-        native.check(self.L.rnc_convex_upsample_fwd(_ptr(flow_low), _ptr(mask_cl), ldm, ws.B, ws.H8, ws.W8, _ptr(out),
-                                                    _stream()), "convex_upsample")
+        with _Timed(self, "convex"):
+            native.check(self.L.rnc_convex_upsample_fwd(_ptr(flow_low), _ptr(mask_cl), ldm, ws.B, ws.H8, ws.W8, _ptr(out),
+                                                        _stream()), "convex_upsample")
         return out
 
     def ncup_from_lowres(self, ws, pu, x_lowres, guid_ptr, ldg, out_scale):
