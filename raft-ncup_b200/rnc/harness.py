@@ -2,8 +2,10 @@
 validate_kitti, :25-55 create_sintel_submission with warm start), runnable on any iterable of samples — the datasets
 themselves are out of scope (no data offline), so `bench.py` / the tests feed synthetic pairs.
 
-Differences from the reference, all behaviour-preserving: pairs are evaluated in batches instead of one at a time (the
-model's batch items are independent), and the warm-start forward interpolation runs on the GPU.
+Differences from the reference, all behaviour-preserving: pairs of equal size are evaluated in batches instead of one at a
+time (the model's batch items are independent; frames of a different size — KITTI's vary — start a new batch), and the
+warm-start forward interpolation runs on the GPU.  Metrics aggregate exactly as the reference's loops do: Sintel-style
+(`valid` absent) pools all pixels (evaluate.py:131-137), KITTI-style averages per-image means (evaluate.py:172-179).
 """
 import numpy as np
 import torch
@@ -13,10 +15,11 @@ from utils.utils import InputPadder, forward_interpolate
 
 @torch.no_grad()
 def validate(model, samples, iters=32, mode="sintel", batch_size=8, device="cuda"):
-    """samples: iterable of (image1 [3,H,W], image2 [3,H,W], flow_gt [2,H,W], valid [H,W] or None), all the same size.
+    """samples: iterable of (image1 [3,H,W], image2 [3,H,W], flow_gt [2,H,W], valid [H,W] or None).
     Returns the metrics validate_sintel / validate_kitti print: EPE, 1px/3px/5px, and KITTI F1 when `valid` is given."""
     model.eval()
     epe_all, f1_all, batch = [], [], []
+    epe_img = []                                            # KITTI: per-image mean EPE (evaluate.py:172)
 
     def flush():
         if not batch:
@@ -36,19 +39,24 @@ def validate(model, samples, iters=32, mode="sintel", batch_size=8, device="cuda
                 val = valid.view(-1) >= 0.5
                 e = epe.view(-1)
                 out = ((e > 3.0) & ((e / mag) > 0.05)).float()
+                epe_img.append(e[val].mean().item())
                 epe_all.append(e[val].numpy())
                 f1_all.append(out[val].numpy())
         batch.clear()
 
     for s in samples:
-        batch.append(s if len(s) == 4 else (s[0], s[1], s[2], None))
+        s = s if len(s) == 4 else (s[0], s[1], s[2], None)
+        if batch and batch[0][0].shape != s[0].shape:       # frame sizes differ (KITTI): close the batch
+            flush()
+        batch.append(s)
         if len(batch) == batch_size:
             flush()
     flush()
     e = np.concatenate(epe_all)
     res = {"epe": float(np.mean(e)), "1px": float(np.mean(e < 1)), "3px": float(np.mean(e < 3)), "5px": float(np.mean(e < 5))}
     if f1_all:
-        res["f1"] = float(100 * np.mean(np.concatenate(f1_all)))
+        res["epe"] = float(np.mean(epe_img))                # evaluate.py:178: mean of the per-image means
+        res["f1"] = float(100 * np.mean(np.concatenate(f1_all)))   # evaluate.py:175,179: pooled over all valid pixels
     return res
 
 

@@ -48,10 +48,10 @@ def test_validate_metrics_with_a_stub_model():
             return flow[:, :, ::8, ::8], flow
     g = torch.Generator().manual_seed(0)
     samples = []
-    for _ in range(5):
+    for k in range(5):
         a, b = torch.rand(3, 20, 30, generator=g) * 4, torch.rand(3, 20, 30, generator=g) * 4
         gt = (a[:2] - b[:2]) + torch.randn(2, 20, 30, generator=g)
-        samples.append((a, b, gt, (torch.rand(20, 30, generator=g) > 0.3).float()))
+        samples.append((a, b, gt, (torch.rand(20, 30, generator=g) > 0.3 + 0.1 * k).float()))   # valid counts differ per image
     res = validate(Stub(), [s[:3] for s in samples], iters=1, batch_size=2, device="cpu")
     e = torch.cat([torch.sum((s[0][:2] - s[1][:2] - s[2]) ** 2, 0).sqrt().view(-1) for s in samples])
     assert abs(res["epe"] - e.mean().item()) < 1e-6 and abs(res["3px"] - (e < 3).float().mean().item()) < 1e-6
@@ -61,9 +61,14 @@ def test_validate_metrics_with_a_stub_model():
         ee = torch.sum((a[:2] - b[:2] - gt) ** 2, 0).sqrt().view(-1)
         mag = torch.sum(gt ** 2, 0).sqrt().view(-1)
         m = v.view(-1) >= 0.5
-        ek.append(ee[m])
+        ek.append(ee[m].mean().item())                      # evaluate.py:172: per-image mean ...
         f1.append(((ee > 3) & (ee / mag > 0.05)).float()[m])
-    assert abs(resk["epe"] - torch.cat(ek).mean().item()) < 1e-6 and abs(resk["f1"] - 100 * torch.cat(f1).mean().item()) < 1e-4
+    assert abs(resk["epe"] - sum(ek) / len(ek)) < 1e-6      # ... averaged over images (evaluate.py:178)
+    assert abs(resk["f1"] - 100 * torch.cat(f1).mean().item()) < 1e-4
+    # frames of different sizes (KITTI) are batched by shape instead of failing in torch.stack
+    odd = (torch.rand(3, 16, 40, generator=g), torch.rand(3, 16, 40, generator=g), torch.zeros(2, 16, 40), torch.ones(16, 40))
+    resm = validate(Stub(), samples[:2] + [odd] + samples[2:], iters=1, mode="kitti", batch_size=4, device="cpu")
+    assert np.isfinite(resm["epe"])
 
 
 def test_load_checkpoint_strips_dataparallel_prefix():
