@@ -82,7 +82,8 @@ constexpr int kSmemB = kStages * kBStage;                    // 64 KB
 // that the gather's scalar loads (lane address = 68*pixel + skew + window offset, window offset ~ pixel's x) hit 32 distinct
 // banks: bank = 5*lane + spread (mod 32)
 constexpr int kScrStride = 68, kScrSkew = 16;
-constexpr int kSmemScratch = (128 * kScrStride + kScrSkew) * 4 + 64;   // 34 KB (+ pad to a 128-byte multiple)
+constexpr int kScrWarp = 32 * kScrStride + kScrSkew;         // words per epilogue warp (its 16 skewed pixels run 16 words past 32*68)
+constexpr int kSmemScratch = 4 * kScrWarp * 4;               // 34.25 KB
 // output tile of one (tile, level) unit: [plane hi | lo][128 px][88 halves], dense = the TMA store's box {88, 16, 2} per warp
 constexpr int kStgPlane = 128 * kLvlStride * 2;              // 22 KB
 constexpr int kSmemStage = 2 * kStgPlane;                    // 44 KB
@@ -131,7 +132,7 @@ template <int BW>
 __device__ __forceinline__ void lookup_level_rows(const EpiCtx& c, int& ch, int l, bool live, int ox, int oy, float ax, float ay) {
   const Params& p = c.p;
   const int cr = chunk_rows(l);
-  float* sc = c.scratch + c.ml * kScrStride + ((c.ml >> 4) & 1) * kScrSkew;   // thread-private: two box rows of 32 words
+  float* sc = c.scratch + c.lg * kScrWarp + c.lane * kScrStride + (c.lane >> 4) * kScrSkew;   // thread-private: two box rows of 32 words
   __half* sth = c.stage + c.ml * kLvlStride;                  // this pixel's row of the level's output tile, hi plane
   __half* stl = sth + 128 * kLvlStride;                       // lo plane
   // window row j of this pixel is complete: taps (0..7, j) -> one 16-byte store per plane, tap (8, j) -> the tail
