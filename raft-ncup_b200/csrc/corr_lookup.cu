@@ -49,19 +49,13 @@ __device__ __forceinline__ float dot16(const float (&a)[kChunk], const float* __
 __global__ void __launch_bounds__(kThreads, 2)
 corr_lookup_tile_kernel(const float* __restrict__ f1_cl, const float* __restrict__ f2_pyr,
                         const float* __restrict__ coords, int B, int D, int H, int W, int levels,
-                        float* __restrict__ out, int layout, int ldo, __half* __restrict__ out_lo,
-                        const int* __restrict__ flags, int ftx, int fty, int lvl_stride) {
+                        float* __restrict__ out, int layout, int ldo, __half* __restrict__ out_lo, int lvl_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LookupSmem& sm = *reinterpret_cast<LookupSmem*>(smem_raw);
 
   const int tid = threadIdx.x;
   const int p = tid >> 2, s = tid & 3;
   const int b = blockIdx.z;
-  // fallback mode: only the 8x16 tiles flagged by the tensor-core kernel are recomputed here
-  if (flags != nullptr) {                // per 8x16 tile: one flag per pyramid level, any set -> recompute the tile
-    const int4 f = reinterpret_cast<const int4*>(flags)[(b * fty + blockIdx.y) * ftx + (blockIdx.x >> 1)];
-    if ((f.x | f.y | f.z | f.w) == 0) return;
-  }
   const int py = blockIdx.y * kTile + (p >> 3), px = blockIdx.x * kTile + (p & 7);
   const bool valid = py < H && px < W;
   const int P = H * W;
@@ -205,8 +199,7 @@ using namespace rnc;
 
 static int lookup_launch(const float* f1_cl, const float* f2_pyr, const float* coords,
                          int B, int D, int H, int W, int levels, int radius,
-                         float* out, int layout, int ldo, __half* out_lo, void* stream,
-                         const int* flags = nullptr, int ftx = 0, int fty = 0, int lvl_stride = kS * kS) {
+                         float* out, int layout, int ldo, __half* out_lo, void* stream, int lvl_stride = kS * kS) {
   if (B <= 0 || H <= 0 || W <= 0 || D <= 0 || (D % kChunk) != 0) return RNC_ERR_BAD_SHAPE;
   if (levels < 1 || levels > 4 || (H >> (levels - 1)) < 1 || (W >> (levels - 1)) < 1) return RNC_ERR_BAD_SHAPE;
   if (radius != kR) return RNC_ERR_UNSUPPORTED;
@@ -218,16 +211,8 @@ static int lookup_launch(const float* f1_cl, const float* f2_pyr, const float* c
   if (int st = ensure_dyn_smem(corr_lookup_tile_kernel, (int)sizeof(LookupSmem), &attr_done)) return st;
   dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, B);
   corr_lookup_tile_kernel<<<grid, kThreads, sizeof(LookupSmem), as_stream(stream)>>>(
-      f1_cl, f2_pyr, coords, B, D, H, W, levels, out, layout, ldo, out_lo, flags, ftx, fty, lvl_stride);
+      f1_cl, f2_pyr, coords, B, D, H, W, levels, out, layout, ldo, out_lo, lvl_stride);
   return after_launch();
-}
-
-// used by corr_lookup_umma.cu
-int rnc_corr_lookup_fallback_split(const float* f1_cl, const float* f2_pyr, const float* coords, int B, int D, int H, int W,
-                                   int levels, void* out_hi, void* out_lo, int ldo, int lvl_stride, const int* flags,
-                                   int flag_tiles_x, int flag_tiles_y, void* stream) {
-  return lookup_launch(f1_cl, f2_pyr, coords, B, D, H, W, levels, kR, static_cast<float*>(out_hi), 2, ldo,
-                       static_cast<__half*>(out_lo), stream, flags, flag_tiles_x, flag_tiles_y, lvl_stride);
 }
 
 extern "C" int rnc_corr_lookup_fwd(const float* f1_cl, const float* f2_pyr, const float* coords,
@@ -241,5 +226,5 @@ extern "C" int rnc_corr_lookup_split_fwd(const float* f1_cl, const float* f2_pyr
                                          int B, int D, int H, int W, int levels, int radius,
                                          void* out_hi, void* out_lo, int ldo, int lvl_stride, void* stream) {
   return lookup_launch(f1_cl, f2_pyr, coords, B, D, H, W, levels, radius, static_cast<float*>(out_hi), 2, ldo,
-                       static_cast<__half*>(out_lo), stream, nullptr, 0, 0, lvl_stride);
+                       static_cast<__half*>(out_lo), stream, lvl_stride);
 }

@@ -26,8 +26,8 @@
 // so the 8 values a thread produces per window row are ONE aligned 16-byte store per plane (conflict-free at the 176-byte
 // pixel pitch) instead of 9 scattered words, and no second pass re-reads / re-packs the level.
 //
-// Tiles whose windows do not fit the fixed boxes (incoherent flow) are flagged and recomputed by the exact CUDA-core
-// kernel (corr_lookup.cu), so the result never depends on the coherence assumption.
+// Units whose windows do not fit the fixed boxes (incoherent flow) are flagged and recomputed exactly in fp32 by the same
+// CTA after its tensor-core units (exact_unit), so the result never depends on the coherence assumption.
 //
 // Measured on B200 (B=8, 55x128, profiles/): the three engines are balanced within 2x of each other — L2->SM operand
 // traffic ~45 us, tensor pipe ~45 us, epilogue ~70 us per launch when each runs alone, ~95 us together.
@@ -53,20 +53,29 @@ constexpr int kS = 9, kG = 10, kR = 4;
 // per-level box: width, rows per chunk, chunks   (union boxes seen on the benchmark stimuli at iteration 31: 28x24, 19x17,
 // 15x14, 13x12; anything larger is handled by the exact fallback kernel)
 // boxes: 32x24, 24x20, 16x16, 16x14 positions = chunks of 256, 240, 256, 224 MMA columns
+#ifndef RNC_LOOKUP_CHUNKN
+#define RNC_LOOKUP_CHUNKN 192    // 3 stages of 24 KB beat 2 of 32 KB (70.6 vs 75.9 us per B=8 launch): more loads in flight
+#endif
 __host__ __device__ constexpr int box_w(int l) { return l == 0 ? 32 : l == 1 ? 24 : 16; }
+#if RNC_LOOKUP_CHUNKN == 256
 __host__ __device__ constexpr int chunk_rows(int l) { return l == 0 ? 8 : l == 1 ? 10 : l == 2 ? 16 : 14; }
 __host__ __device__ constexpr int n_chunks(int l) { return l == 0 ? 3 : l == 1 ? 2 : 1; }
+#else   // chunks of <= 192 MMA columns (24 KB stages: a third stage fits): 6x32, 8x24, 12x16, 12x16
+__host__ __device__ constexpr int chunk_rows(int l) { return l == 0 ? 6 : l == 1 ? 8 : 12; }
+__host__ __device__ constexpr int n_chunks(int l) { return l == 0 ? 4 : l == 1 ? 3 : 2; }
+#endif
 __host__ __device__ constexpr int box_h(int l) { return chunk_rows(l) * n_chunks(l); }
 __host__ __device__ constexpr int chunk_n(int l) { return box_w(l) * chunk_rows(l); }
-#ifndef RNC_LOOKUP_TMAROWS
-#define RNC_LOOKUP_TMAROWS 2
+static_assert(chunk_rows(0) <= 16 && chunk_rows(1) <= 16 && chunk_rows(2) <= 16 && chunk_rows(3) <= 16, "one box kind per even row count");
+#ifndef RNC_LOOKUP_L2HINT
+#define RNC_LOOKUP_L2HINT 0      // evict_last on the feature loads measured 3 % slower on B200 (81.6 vs 78.8 us per B=8 launch)
 #endif
 #ifndef RNC_LOOKUP_STAGES
-#define RNC_LOOKUP_STAGES 2
+#define RNC_LOOKUP_STAGES (RNC_LOOKUP_CHUNKN == 192 ? 3 : 2)
 #endif
 constexpr int kStages = RNC_LOOKUP_STAGES;   // B ring (a third stage does not fit beside the two-row scratch and measures the same)
 constexpr int kATile = 128 * 64 * 2;     // 16 KB per K block
-constexpr int kBStage = 256 * 64 * 2;    // 32 KB: 256 positions x 64 halves
+constexpr int kBStage = RNC_LOOKUP_CHUNKN * 64 * 2;    // 32 KB: 256 positions x 64 halves (24 KB with 192-column chunks)
 constexpr int kLvlStride = 88;           // channels per level in the output row (81 taps + 7 zero pads): 16-byte groups
 #ifndef RNC_LOOKUP_TIRING
 #define RNC_LOOKUP_TIRING 4
@@ -95,13 +104,19 @@ constexpr int kSmemTotal = kSmemA + kSmemB + kSmemScratch + kSmemStage + 1024 + 
 #endif
 
 struct Params {
+  const float* f1_cl; const float* f2_pyr;   // fp32 originals: exact path of the units whose windows do not fit the boxes
   const float* coords;                 // [B][2][H][W]
   __half* out_hi; __half* out_lo; int ldo;
   int* flags;                          // [tiles][4 levels]: 1 = recompute this tile with the exact kernel
   int B, H, W, tiles_x, tiles_y;
-  int tile_major;                      // unit order: 1 = the four levels of a tile back to back on one CTA (A loaded once per tile)
+  int tile_major;                      // unit schedule: 0 level-major, 1 tile-major, 2 hybrid (see unit_at)
   float scale;
 };
+
+// fmap2^l boxes of every even row count up to 16 per level: the rows a chunk needs are ONE TMA operation (the per-operation
+// cost dominates: 2-row boxes measured 49.6 us per B=8 launch for the loads alone, whole-chunk boxes 40.9 us with more bytes)
+constexpr int kBoxKinds = 8;
+struct LevelMaps { CUtensorMap m[kLevels][kBoxKinds]; };
 
 struct TileInfo {                      // shared: origin of the unit's union box (0,0 when no window is live), the box rows
   int bx0, by0, overflow, nrows;       // actually needed (even, <= box_h; 0 = no live window): only those are loaded / multiplied
@@ -273,20 +288,108 @@ __device__ __forceinline__ void lookup_epilogue(const EpiCtx& c, int& ch, int l,
 #endif
 }
 
-// Work units.  A unit is (tile, level): 3, 2, 1, 1 accumulator chunks.  Units are listed level-major (all level-0 units
-// first = longest first) and dealt to the CTAs in snake order (round k runs left-to-right for even k, right-to-left for
-// odd k): a single image (56 tiles of 7 chunks) still fills all 148 SMs, the busiest CTA getting 3 chunks, and for B=8
-// the busiest CTA gets 23 chunks where whole tiles would give it 28.  The alternative tile-major order (the four levels
-// of a tile back to back on one CTA, A loaded once per tile) is selectable from the host.
-// Returns the k-th unit of this CTA or -1 (none in round k).
-__device__ __forceinline__ int unit_at(int k, int nunits, int tile_major) {
+// Work units.  A unit is (tile, level): 3, 2, 1, 1 accumulator chunks.  Schedules (Params.tile_major):
+//   0  level-major: units listed level-major (all level-0 units first = longest first) and dealt to the CTAs in snake order
+//      (round k runs left-to-right for even k, right-to-left for odd k); every unit loads its own A tile
+//   1  tile-major: the four levels of a tile back to back on one CTA, A loaded once per tile (4x less A traffic, no A reload
+//      bubble between levels), but whole tiles balance badly (B=8: 448 tiles on 148 CTAs -> the busiest CTA gets 4)
+//   2  hybrid (default): the complete rounds of tiles (floor(ntiles / CTAs) per CTA) tile-major, the remaining tiles
+//      level-major over all CTAs.  B=8: 3 tile-major rounds + 16 units -> busiest CTA 24 chunks (level-major: 23) with a
+//      quarter of the A loads; a single image (56 tiles < 148 CTAs) is all level-major and still fills the SMs.
+// Returns the k-th unit of this CTA as (tile-major flag << 30) | (level * ntiles + tile), or -1 (none in round k).
+constexpr int kUnitTm = 1 << 30;
+__device__ __forceinline__ int unit_id(int u) { return u & (kUnitTm - 1); }
+__device__ __forceinline__ bool unit_tm(int u) { return (u & kUnitTm) != 0; }
+__device__ __forceinline__ int unit_at(int k, int ntiles, int mode) {
   const int G = gridDim.x, c = blockIdx.x;
-  if (tile_major) {
-    const int ntiles = nunits / kLevels, tile = (k / kLevels) * G + c;
-    return tile < ntiles ? (k % kLevels) * ntiles + tile : -1;
+  const int full = mode == 0 ? 0 : mode == 1 ? (ntiles + G - 1) / G : ntiles / G;      // tile-major rounds
+  if (k < full * kLevels) {
+    const int tile = (k / kLevels) * G + c;
+    return tile < ntiles ? kUnitTm | ((k % kLevels) * ntiles + tile) : -1;
   }
-  const int g = k * G + ((k & 1) ? G - 1 - c : c);
-  return g < nunits ? g : -1;
+  if (mode == 1) return -1;
+  const int kk = k - full * kLevels, done = full * G, rem = ntiles - done;             // remaining tiles, level-major snake
+  const int g = kk * G + ((kk & 1) ? G - 1 - c : c);
+  if (g >= rem * kLevels) return -1;
+  const int l = g / rem;
+  return l * ntiles + done + (g - l * rem);
+}
+__device__ __forceinline__ int unit_rounds(int ntiles, int mode) {
+  const int G = gridDim.x;
+  if (mode == 1) return ((ntiles + G - 1) / G) * kLevels;
+  const int full = mode == 0 ? 0 : ntiles / G;
+  return full * kLevels + ((ntiles - full * G) * kLevels + G - 1) / G;
+}
+
+// Exact fp32 recomputation of one (tile, level) unit whose windows did not fit the fixed box (incoherent flow, e.g. a motion
+// boundary): warp = pixel, the 100 lattice dot products of the pixel's window straight from the fp32 feature maps (lane = 8
+// channels, positions outside the level image contribute 0 = grid_sample's zero padding), then the bilinear blend of
+// SURVEY.md Appendix A.1 and the same hi/lo split output in the resident channel order.  Runs on all warps of the CTA after
+// its tensor-core units: results never depend on a coherence assumption, and there is no second kernel launch.
+__device__ __noinline__ void exact_unit(const Params& p, int l, int tile, float* gsm, int warp, int lane, int nwarps) {
+  const int tpi = p.tiles_x * p.tiles_y, HW = p.H * p.W;
+  const int b = tile / tpi, tr = tile - b * tpi;
+  const int y0 = (tr / p.tiles_x) * kTY, x0 = (tr % p.tiles_x) * kTX;
+  const int Hl = p.H >> l, Wl = p.W >> l;
+  size_t off = 0;
+  for (int k = 0; k < l; ++k) off += static_cast<size_t>(p.B) * (p.H >> k) * (p.W >> k) * kD;
+  const float* f2l = p.f2_pyr + off + static_cast<size_t>(b) * Hl * Wl * kD;
+  const float inv = 1.f / static_cast<float>(1 << l);
+  float* g = gsm + warp * 104;
+  for (int px = warp; px < kTY * kTX; px += nwarps) {
+    const int qy = y0 + (px >> 4), qx = x0 + (px & 15);
+    if (qy >= p.H || qx >= p.W) continue;                       // warp-uniform
+    const float cx = clamp_coord(__ldg(p.coords + (static_cast<size_t>(b) * 2 + 0) * HW + qy * p.W + qx));
+    const float cy = clamp_coord(__ldg(p.coords + (static_cast<size_t>(b) * 2 + 1) * HW + qy * p.W + qx));
+    const float sx = cx * inv, sy = cy * inv;
+    const float fx0 = floorf(sx), fy0 = floorf(sy), ax = sx - fx0, ay = sy - fy0;
+    const int ix0 = static_cast<int>(fx0) - kR, iy0 = static_cast<int>(fy0) - kR;
+    const float4* f1p = reinterpret_cast<const float4*>(p.f1_cl + (static_cast<size_t>(b) * HW + qy * p.W + qx) * kD);
+    const float4 a0 = __ldg(f1p + lane), a1 = __ldg(f1p + 32 + lane);
+    // lattice (a = x offset, c = y offset) -> g[a*10 + c]; five positions per pass so that their loads are in flight together
+    for (int c = 0; c < kG; ++c) {
+      const int Y = iy0 + c;
+      const bool rowin = Y >= 0 && Y < Hl;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float4 b0[5], b1[5];
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+          const int X = ix0 + half * 5 + u;
+          const bool in = rowin && X >= 0 && X < Wl;              // warp-uniform
+          const float4* q = reinterpret_cast<const float4*>(f2l + (static_cast<size_t>(in ? Y : 0) * Wl + (in ? X : 0)) * kD);
+          b0[u] = in ? __ldg(q + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+          b1[u] = in ? __ldg(q + 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+          float d = a0.x * b0[u].x;
+          d = fmaf(a0.y, b0[u].y, d); d = fmaf(a0.z, b0[u].z, d); d = fmaf(a0.w, b0[u].w, d);
+          d = fmaf(a1.x, b1[u].x, d); d = fmaf(a1.y, b1[u].y, d); d = fmaf(a1.z, b1[u].z, d); d = fmaf(a1.w, b1[u].w, d);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+          if (lane == 0) g[(half * 5 + u) * kG + c] = d * p.scale;
+        }
+      }
+    }
+    __syncwarp();
+    const size_t base = (static_cast<size_t>(b) * HW + qy * p.W + qx) * p.ldo + l * kLvlStride;
+    for (int t = lane; t < kS * kS; t += 32) {
+      const int i = t / kS, j = t - i * kS;
+      const float* gp = g + i * kG + j;
+      const float v = (1.f - ax) * (1.f - ay) * gp[0] + ax * (1.f - ay) * gp[kG] + (1.f - ax) * ay * gp[1] + ax * ay * gp[kG + 1];
+      uint32_t hh, ll;
+      split_pair(v, 0.f, hh, ll);
+      const size_t k = base + (i < 8 ? j * 8 + i : 72 + j);
+      reinterpret_cast<unsigned short*>(p.out_hi)[k] = static_cast<unsigned short>(hh & 0xffffu);
+      reinterpret_cast<unsigned short*>(p.out_lo)[k] = static_cast<unsigned short>(ll & 0xffffu);
+    }
+    if (lane < kLvlStride - kS * kS) {                          // the level's zero pads
+      reinterpret_cast<unsigned short*>(p.out_hi)[base + kS * kS + lane] = 0;
+      reinterpret_cast<unsigned short*>(p.out_lo)[base + kS * kS + lane] = 0;
+    }
+    __syncwarp();
+  }
 }
 
 // Persistent kernel: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The three roles run decoupled
@@ -296,9 +399,8 @@ __device__ __forceinline__ int unit_at(int k, int nunits, int tile_major) {
 //   warp 1      MMA issuer; TMEM accumulators are double buffered across chunks and tiles
 //   warps 2..   epilogue
 __global__ void __launch_bounds__(kThreads, 1)
-corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_constant__ CUtensorMap mL0,
-                        const __grid_constant__ CUtensorMap mL1, const __grid_constant__ CUtensorMap mL2,
-                        const __grid_constant__ CUtensorMap mL3, const __grid_constant__ CUtensorMap mOutHi,
+corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_constant__ LevelMaps mLv,
+                        const __grid_constant__ CUtensorMap mOutHi,
                         const __grid_constant__ CUtensorMap mOutLo, const Params p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned, stays in the shared window
@@ -316,6 +418,7 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
   uint64_t* ti_full = acc_empty + 2;                          // [kTiRing]
   uint64_t* ti_empty = ti_full + kTiRing;                     // [kTiRing]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ti_empty + kTiRing);
+  int* ov_count = reinterpret_cast<int*>(tmem_slot + 1);      // units of this CTA that overflowed their box
   TileInfo* ti = reinterpret_cast<TileInfo*>(tmem_slot + 2);  // [kTiRing]
 
   pdl_trigger();
@@ -325,6 +428,7 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
   const int HW = p.H * p.W;
 
   if (threadIdx.x == 0) {
+    *ov_count = 0;
     for (int kb = 0; kb < kKB; ++kb) { mbar_init(&a_full[kb], 1); mbar_init(&a_empty[kb], 1); }
     for (int s = 0; s < kStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
@@ -339,13 +443,16 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
   pdl_wait();                          // coords1 of the previous iteration's flow update is visible from here
 
   const int nunits = ntiles * kLevels;
-  const int tm = p.tile_major;
-  const int rounds = tm ? ((ntiles + gridDim.x - 1) / gridDim.x) * kLevels : (nunits + gridDim.x - 1) / gridDim.x;
+  const int sched = p.tile_major;
+  const int rounds = unit_rounds(ntiles, sched);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer (warp-uniform loops, one elected lane issues)
     // lane owns pixels lane, lane+32, lane+64, lane+96 of the tile for the box reduction
     float pcx[4], pcy[4];
+#if RNC_LOOKUP_L2HINT
+    const uint64_t pol_keep = l2_policy_evict_last();   // the feature maps are re-read by every tile and every iteration
+#endif
     auto load_coords = [&](int tile, float (&ox)[4], float (&oy)[4]) {
       const int b = tile / tpi, tr = tile - b * tpi;
       const int y0 = (tr / p.tiles_x) * kTY, x0 = (tr % p.tiles_x) * kTX;
@@ -360,7 +467,7 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
     // record of one unit: union box origin, rows needed, overflow
     struct Rec { int bx0, by0, nrows, ov; };
     auto make_rec = [&](int unit, const float (&ux)[4], const float (&uy)[4]) {
-      const int l = unit / ntiles;
+      const int l = unit_id(unit) / ntiles;
       const float inv = 1.f / static_cast<float>(1 << l);
       int lx0 = 0x7fffffff, ly0 = 0x7fffffff, lx1 = -0x7fffffff, ly1 = -0x7fffffff;
 #pragma unroll
@@ -389,8 +496,9 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
       mbar_wait(&ti_empty[slot], ((n >> kTiShift) & 1) ^ 1);
       if (lane == 0) {
         ti[slot].bx0 = r.bx0; ti[slot].by0 = r.by0; ti[slot].overflow = r.ov; ti[slot].nrows = r.nrows;
-        const int l = unit / ntiles;
-        p.flags[(unit - l * ntiles) * kLevels + l] = r.ov;
+        const int l = unit_id(unit) / ntiles;
+        p.flags[(unit_id(unit) - l * ntiles) * kLevels + l] = r.ov;
+        if (r.ov) *ov_count += 1;
         mbar_arrive(&ti_full[slot]);         // release: the unit record is visible to the waiters
       }
       __syncwarp();
@@ -399,18 +507,28 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
     // The record of unit k+1 is computed and published while unit k's loads are in flight (after its first kStages B
     // loads, when the ring is full and this warp would only wait), from coords fetched one unit earlier: nothing but
     // barrier waits sits between the last load of a unit and the first load of the next.
-    int unit = unit_at(0, nunits, tm), next = -1;
+    // (a CTA's units are consecutive k: tile-major rounds first, then at most a run of remainder rounds)
+    int unit = unit_at(0, ntiles, sched), next = -1;
     Rec cur = {0, 0, 0, 0}, nxt = {0, 0, 0, 0};
+    int kfirst = 0;
+    while (unit < 0 && kfirst + 1 < rounds) unit = unit_at(++kfirst, ntiles, sched);
+    auto next_unit = [&](int& kk) {              // first valid unit after round kk (rounds with no unit for this CTA are skipped)
+      int u = -1;
+      while (u < 0 && kk + 1 < rounds) u = unit_at(++kk, ntiles, sched);
+      return u;
+    };
+    int knext = kfirst;
     if (unit >= 0) {
-      load_coords(unit % ntiles, pcx, pcy);
+      load_coords(unit_id(unit) % ntiles, pcx, pcy);
       cur = make_rec(unit, pcx, pcy);
       publish(unit, cur);
-      next = unit_at(1, nunits, tm);
-      if (next >= 0) load_coords(next % ntiles, pcx, pcy);
+      next = next_unit(knext);
+      if (next >= 0) load_coords(unit_id(next) % ntiles, pcx, pcy);
     }
     int it = 0, na = 0;
-    for (int k = 0; unit >= 0; ++k) {
-      const int l = unit / ntiles, tile = unit - l * ntiles;
+    while (unit >= 0) {
+      const bool tm = unit_tm(unit);
+      const int l = unit_id(unit) / ntiles, tile = unit_id(unit) - l * ntiles;
       const int b = tile / tpi, tr = tile - b * tpi;
       const int y0 = (tr / p.tiles_x) * kTY, x0 = (tr % p.tiles_x) * kTX;
       const int bx0 = cur.bx0, by0 = cur.by0, nrows = cur.nrows;
@@ -425,7 +543,11 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
             mbar_arrive(&a_full[kb]);
 #else
             mbar_expect_tx(&a_full[kb], kATile);
+#if RNC_LOOKUP_L2HINT
+            tma_load_4d_hint(sA + kb * kATile, &mF1, &a_full[kb], kb * 64, x0, y0, b, pol_keep);
+#else
             tma_load_4d(sA + kb * kATile, &mF1, &a_full[kb], kb * 64, x0, y0, b);
+#endif
 #endif
           }
           __syncwarp();
@@ -440,14 +562,14 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
         if (next >= 0) {
           nxt = make_rec(next, pcx, pcy);
           publish(next, nxt);
-          after = unit_at(k + 2, nunits, tm);
-          if (after >= 0) load_coords(after % ntiles, pcx, pcy);
+          after = next_unit(knext);
+          if (after >= 0) load_coords(unit_id(after) % ntiles, pcx, pcy);
         }
       };
       if (!skip) {
         // B: only the box rows some window needs, as 2-row TMA boxes (2 * bw positions = a multiple of 1024 bytes of the
         // SWIZZLE_128B stage, so the pieces tile the stage exactly as one big box would)
-        const CUtensorMap* map = l == 0 ? &mL0 : l == 1 ? &mL1 : l == 2 ? &mL2 : &mL3;
+        const CUtensorMap* map = &mLv.m[l][0];
         const int cr = chunk_rows(l), bw = box_w(l);
         int issued = 0;
         for (int c = 0; c * cr < nrows; ++c) {
@@ -459,13 +581,11 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
 #ifdef RNC_PROBE_NOLOAD
               mbar_arrive(&b_full[s]);
 #else
-#if RNC_LOOKUP_TMAROWS == 2
               mbar_expect_tx(&b_full[s], rows * bw * 128);
-              for (int r2 = 0; r2 < rows; r2 += 2)
-                tma_load_4d(sB + s * kBStage + r2 * bw * 128, map, &b_full[s], kb * 64, bx0, by0 + c * cr + r2, b);
+#if RNC_LOOKUP_L2HINT
+              tma_load_4d_hint(sB + s * kBStage, map + (rows >> 1) - 1, &b_full[s], kb * 64, bx0, by0 + c * cr, b, pol_keep);
 #else
-              mbar_expect_tx(&b_full[s], cr * bw * 128);
-              tma_load_4d(sB + s * kBStage, map, &b_full[s], kb * 64, bx0, by0 + c * cr, b);
+              tma_load_4d(sB + s * kBStage, map + (rows >> 1) - 1, &b_full[s], kb * 64, bx0, by0 + c * cr, b);   // rows is even
 #endif
 #endif
             }
@@ -482,9 +602,10 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
     const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
     int it = 0, ch = 0, n = 0, na = 0;
     for (int k = 0; k < rounds; ++k) {
-      const int unit = unit_at(k, nunits, tm);
+      const int unit = unit_at(k, ntiles, sched);
       if (unit < 0) continue;
-      const int l = unit / ntiles;
+      const bool tm = unit_tm(unit);
+      const int l = unit_id(unit) / ntiles;
       const int slot = n & (kTiRing - 1);
       mbar_wait(&ti_full[slot], (n >> kTiShift) & 1);
       const int ov = ti[slot].overflow, nrows = ti[slot].nrows;
@@ -556,16 +677,16 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
       *reinterpret_cast<uint4*>(stage + (128 + ml) * kLvlStride + 80) = z;
     }
 #endif
-    int unit = unit_at(0, nunits, tm);
-    if (unit >= 0) load_coord(unit % ntiles, ncx, ncy, nvalid);
+    int unit = unit_at(0, ntiles, sched);
+    if (unit >= 0) load_coord(unit_id(unit) % ntiles, ncx, ncy, nvalid);
     int ch = 0, n = 0;
     for (int k = 0; k < rounds; ++k) {
       const int cur = unit;
       cx = ncx; cy = ncy; valid = nvalid;
-      unit = unit_at(k + 1, nunits, tm);
-      if (unit >= 0) load_coord(unit % ntiles, ncx, ncy, nvalid);
+      unit = k + 1 < rounds ? unit_at(k + 1, ntiles, sched) : -1;
+      if (unit >= 0) load_coord(unit_id(unit) % ntiles, ncx, ncy, nvalid);
       if (cur < 0) continue;
-      const int l = cur / ntiles, tile = cur - l * ntiles;
+      const int l = unit_id(cur) / ntiles, tile = unit_id(cur) - l * ntiles;
       const int b = tile / tpi, tr = tile - b * tpi;
       const int y0 = (tr / p.tiles_x) * kTY, x0 = (tr % p.tiles_x) * kTX;
       const int slot = n & (kTiRing - 1);
@@ -586,6 +707,14 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+  // ---- units of this CTA that overflowed their box (flagged by this CTA's own producer warp): exact path, all warps
+  if (*ov_count == 0) return;                  // the common case: nothing to redo
+  for (int k = 0; k < rounds; ++k) {
+    const int unit = unit_at(k, ntiles, sched);
+    if (unit < 0) continue;
+    const int l = unit_id(unit) / ntiles, tile = unit_id(unit) - l * ntiles;
+    if (p.flags[tile * kLevels + l] != 0) exact_unit(p, l, tile, scratch, warp, lane, kThreads / 32);
   }
 }
 
@@ -631,11 +760,6 @@ static int sm_count() {
   return cached;
 }
 
-// defined in corr_lookup.cu: exact kernel restricted to flagged 8x16 tiles, split-halves output
-int rnc_corr_lookup_fallback_split(const float* f1_cl, const float* f2_pyr, const float* coords, int B, int D, int H, int W,
-                                   int levels, void* out_hi, void* out_lo, int ldo, int lvl_stride, const int* flags,
-                                   int flag_tiles_x, int flag_tiles_y, void* stream);
-
 extern "C" int rnc_corr_lookup_umma_fwd(const void* f1h_cl, const void* f2h_pyr, const float* f1_cl, const float* f2_pyr,
                                         const float* coords, int B, int D, int H, int W, int levels, int radius,
                                         void* out_hi, void* out_lo, int ldo, int lvl_stride, void* workspace,
@@ -651,6 +775,7 @@ extern "C" int rnc_corr_lookup_umma_fwd(const void* f1h_cl, const void* f2h_pyr,
   if (!encode_fn()) return RNC_ERR_UNSUPPORTED;
 
   Params p;
+  p.f1_cl = f1_cl; p.f2_pyr = f2_pyr;
   p.coords = coords;
   p.out_hi = static_cast<__half*>(out_hi); p.out_lo = static_cast<__half*>(out_lo); p.ldo = ldo;
   p.flags = static_cast<int*>(workspace);
@@ -658,13 +783,13 @@ extern "C" int rnc_corr_lookup_umma_fwd(const void* f1h_cl, const void* f2h_pyr,
   p.tiles_x = (W + kTX - 1) / kTX; p.tiles_y = (H + kTY - 1) / kTY;
   p.scale = 1.0f / sqrtf(static_cast<float>(D));
   {
-    // Level-major snake order by default.  Tile-major (A loaded once per tile) measures the same inside the update loop
-    // and 10% slower alone (B=8, 55x128: 0.109 vs 0.097 ms); kept as a developer override, RNC_LOOKUP_SCHED=tile.
+    // Hybrid order by default (see unit_at); RNC_LOOKUP_SCHED=level|tile select the pure orders (developer override).
     static const char* env = getenv("RNC_LOOKUP_SCHED");
-    p.tile_major = env != nullptr && env[0] == 't';
+    p.tile_major = env == nullptr ? 2 : env[0] == 't' ? 1 : env[0] == 'l' ? 0 : 2;
   }
 
   CUtensorMap maps[7];
+  LevelMaps lv;
   bool ok = make_act_map(&maps[0], f1h_cl, kD, kD, B, H, W, kTX, kTY);
   // output planes [B][H][W][ldo] halves: un-swizzled store boxes of one level (88 channels) x 16 x 2 pixels
   ok = ok && make_plain_map(&maps[5], out_hi, ldo, ldo, B, H, W, kLvlStride, kTX, 2);
@@ -672,7 +797,8 @@ extern "C" int rnc_corr_lookup_umma_fwd(const void* f1h_cl, const void* f2h_pyr,
   size_t off = 0;
   for (int l = 0; l < kLevels; ++l) {
     const int Hl = H >> l, Wl = W >> l;
-    ok = ok && make_act_map(&maps[1 + l], static_cast<const __half*>(f2h_pyr) + off, kD, kD, B, Hl, Wl, box_w(l), RNC_LOOKUP_TMAROWS == 2 ? 2 : chunk_rows(l));
+    for (int q = 0; q < kBoxKinds; ++q)
+      ok = ok && make_act_map(&lv.m[l][q], static_cast<const __half*>(f2h_pyr) + off, kD, kD, B, Hl, Wl, box_w(l), 2 * (q + 1));
     off += static_cast<size_t>(B) * Hl * Wl * kD;
   }
   if (!ok) return RNC_ERR_BAD_SHAPE;
@@ -681,11 +807,7 @@ extern "C" int rnc_corr_lookup_umma_fwd(const void* f1h_cl, const void* f2h_pyr,
   if (int st = ensure_dyn_smem(corr_lookup_umma_kernel, kSmemTotal, &done)) return st;
   const int ntiles = B * p.tiles_x * p.tiles_y;
   const int grid = ntiles * kLevels < sm_count() ? ntiles * kLevels : sm_count();   // persistent: one CTA per SM
-  cudaError_t e = launch_pdl(corr_lookup_umma_kernel, dim3(grid), dim3(kThreads), kSmemTotal, as_stream(stream), maps[0], maps[1], maps[2],
-                             maps[3], maps[4], maps[5], maps[6], p);
+  cudaError_t e = launch_pdl(corr_lookup_umma_kernel, dim3(grid), dim3(kThreads), kSmemTotal, as_stream(stream), maps[0], lv, maps[5], maps[6], p);
   if (e != cudaSuccess) { g_last_cuda_error = static_cast<int>(e); return RNC_ERR_CUDA; }
-  if (int st = after_launch()) return st;
-  // exact recomputation of the tiles the fixed boxes could not cover
-  return rnc_corr_lookup_fallback_split(f1_cl, f2_pyr, coords, B, D, H, W, levels, out_hi, out_lo, ldo, lvl_stride, p.flags,
-                                        p.tiles_x, p.tiles_y, stream);
+  return after_launch();
 }
