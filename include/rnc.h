@@ -322,6 +322,29 @@ int rnc_nconv2d_bwd(const float* data, const float* conf, const float* weight, c
                     float eps, float* g_data, float* g_conf, float* g_weight, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training path (train.py:203-227): backward kernels, exact fp32.
+ *
+ * Gradient of CorrBlock.__call__ (core/corr.py:23-44; the reference back-propagates through the stored 4-D pyramid) w.r.t.
+ * the feature maps.  coords are detached (raft_nc_dbl.py:149): no gradient flows to them.
+ *   g_out    : CL [B][H][W][ldg], channels [0, 324) in the reference order k = l*81 + i*9 + j
+ *   g_f1     : CL [B][H*W][D], written
+ *   g_f2_pyr : pyramid layout of rnc_fmap_prepare, ACCUMULATED with atomics — the caller zero-fills it; finish with
+ *              rnc_pyramid_pool_bwd, which folds levels 3..1 into level 0 (adjoint of the 2x2 average pooling,
+ *              core/corr.py:18-21 applied to features) so that level 0 holds d loss / d fmap2 (CL)
+ */
+int rnc_corr_lookup_bwd(const float* f1_cl, const float* f2_pyr, const float* coords, const float* g_out, int ldg,
+                        int B, int D, int H, int W, int levels, int radius, float* g_f1, float* g_f2_pyr, void* stream);
+int rnc_pyramid_pool_bwd(float* g_f2_pyr, int B, int D, int H, int W, int levels, void* stream);
+
+/* Weight and bias gradient of a channel-last convolution y = conv(x, w) + b (stride 1 or 2, zero padding k/2):
+ *   x  : CL [B][Hin][Win][ldx], cin % 4 == 0;   gy : CL [B][ceil(Hin/s)][ceil(Win/s)][ldg] = d loss / d y
+ *   gw : [kh*kw][cin][ldw] fp32 (the packing of rnc_conv2d_cl_fwd's weight), ACCUMULATED (caller zero-fills)
+ *   gb : [cout], accumulated, may be NULL
+ * The data gradient is rnc_conv2d_cl_fwd on gy (zero-dilated for stride 2) with the flipped, transposed weights. */
+int rnc_conv2d_cl_wgrad(const float* x, int ldx, int cin, const float* gy, int ldg, int cout, int B, int Hin, int Win,
+                        int kh, int kw, int stride, float* gw, int ldw, float* gb, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

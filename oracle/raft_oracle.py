@@ -97,7 +97,7 @@ def corr_lookup(pyr, coords, radius=4):
     n = b * h * w
     side = 2 * radius + 1
     c = coords.permute(0, 2, 3, 1).reshape(n, 2)
-    d = torch.arange(-radius, radius + 1, dtype=torch.float32)
+    d = torch.arange(-radius, radius + 1, dtype=torch.float32, device=coords.device)
     off_i = d.view(side, 1).expand(side, side).reshape(1, -1)  # added to x
     off_j = d.view(1, side).expand(side, side).reshape(1, -1)  # added to y
     outs = []
@@ -224,7 +224,7 @@ def nconv2d(data, conf, weight, eps=1e-20):
 def zero_stuff(x, scale=4):
     """core/upsampler.py:179-210 — zeros [B,C,s*h,s*w] with out[..., s//2::s, s//2::s] = x."""
     b, c, h, w = x.shape
-    out = torch.zeros(b, c, h * scale, w * scale, dtype=x.dtype)
+    out = torch.zeros(b, c, h * scale, w * scale, dtype=x.dtype, device=x.device)
     out[:, :, scale // 2::scale, scale // 2::scale] = x
     return out
 
@@ -322,8 +322,8 @@ def raft_forward_graph(sd, image1, image2, iters=12, model="raft_nc_dbl", flow_i
     cnet = basic_encoder(sd, "cnet.", image1, "batch")
     net, inp = torch.tanh(cnet[:, :128]), torch.relu(cnet[:, 128:])
     h8, w8 = image1.shape[2] // 8, image1.shape[3] // 8
-    coords0 = coords_grid(b, h8, w8)
-    coords1 = coords_grid(b, h8, w8)
+    coords0 = coords_grid(b, h8, w8).to(image1.device)     # (device-agnostic: the tests also evaluate this graph in fp32 on the GPU)
+    coords1 = coords_grid(b, h8, w8).to(image1.device)
     if flow_init is not None:
         coords1 = coords1 + flow_init
     if trace is not None:

@@ -442,7 +442,6 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                          // coords1 of the previous iteration's flow update is visible from here
 
-  const int nunits = ntiles * kLevels;
   const int sched = p.tile_major;
   const int rounds = unit_rounds(ntiles, sched);
 

@@ -68,14 +68,16 @@ class _RAFTBase(nn.Module):
             return self._forward(eng, image1, image2, iters, flow_init, test_mode)
 
     def _forward(self, eng, image1, image2, iters, flow_init, test_mode):
-        if self._needs_grad():
-            raise NotImplementedError(
-                "training (autograd through the fused kernels) is not built yet (SURVEY.md §8f-3); "
-                "run inference under torch.no_grad()")
         if iters < 1:
             raise ValueError("iters must be >= 1")
         if hasattr(self, "data_idx"):
             self.data_idx += 1
+        if self._needs_grad():
+            # training path (train.py:215): the same graph with autograd, exact-fp32 kernels forward and backward
+            if image1.shape[2] % 8 or image1.shape[3] % 8:
+                raise ValueError("image height/width must be multiples of 8 (pad with utils.utils.InputPadder, evaluate.py:125)")
+            from .train import raft_forward_train
+            return raft_forward_train(self, image1, image2, iters, flow_init, test_mode)
         B, _, Him, Wim = image1.shape
         if Him % 8 or Wim % 8:
             raise ValueError("image height/width must be multiples of 8 (pad with utils.utils.InputPadder, evaluate.py:125)")
@@ -84,7 +86,8 @@ class _RAFTBase(nn.Module):
         pk = eng.packed_update(self.update_block)
         pu = eng.packed_upsampler(self.upsampler) if self.ncup else None
         if self.ncup and any(isinstance(m, nn.BatchNorm2d) and m.training for m in self.upsampler.modules()):
-            raise NotImplementedError("weights-net BatchNorm in training mode is not built; call .eval() or freeze_bn()")
+            raise NotImplementedError("weights-net BatchNorm with batch statistics needs the training path (enable grad) "
+                                      "or eval mode: call .eval() / freeze_bn()")
         ws = eng.workspace(image1.device, B, H8, W8, pk.has_mask, self.ncup)
         s = _stream()
         amp = bool(getattr(self.args, "mixed_precision", False))
