@@ -485,6 +485,105 @@ def cpu_baseline_subprocess(args):
         return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
+TRAIN_METRIC = "training image-pairs/sec @ 512x384, 12 iters (BASELINE configs[4])"
+
+
+def run_train(args, rank, world, local_rank):
+    """BASELINE configs[4] / SURVEY.md §8e: one optimisation step of raft_nc_dbl per timed step — batch 2 per GPU (16 on 8 GPUs),
+    384x512 synthetic frames, 12 iterations, sequence loss, AdamW + OneCycle, gradient clipping; under torchrun the replicas are
+    DistributedDataParallel over NCCL (one bucketed all-reduce of the 19.6 MB of fp32 gradients per step, overlapped with the
+    backward pass).  Train mode with frozen BatchNorm, as every stage but `chairs` (train.py:185-186)."""
+    import torch.distributed as dist
+    use_product_path()
+    from rnc import native
+    from rnc.synth import build_model
+    from rnc.train import ddp_model, fetch_optimizer, train_step
+    assert torch.cuda.is_available(), "bench.py --mode train needs a GPU"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B, H, W, iters = args.train_batch, 384, 512, 12
+    model = build_model(args.model).to(dev).train()
+    model.freeze_bn()
+    nparams = sum(p.numel() for p in model.parameters())
+    net = ddp_model(model, dev) if world > 1 else model
+    opt, sched = fetch_optimizer(net, lr=1e-4, num_steps=10000)
+    g = torch.Generator().manual_seed(100 + rank)
+    h1 = (torch.rand(B, 3, H, W, generator=g) * 255).pin_memory()
+    h2 = (torch.rand(B, 3, H, W, generator=g) * 255).pin_memory()
+    hgt = (torch.randn(B, 2, H, W, generator=g) * 5).pin_memory()
+    hval = torch.ones(B, H, W).pin_memory()
+
+    def step():
+        im1, im2, gt, val = (t.to(dev, non_blocking=True) for t in (h1, h2, hgt, hval))     # the step's inputs come from the host
+        loss, _ = train_step(net, opt, sched, im1, im2, gt, val, iters=iters, gamma=0.85, clip=1.0, return_metrics=False)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    native.launch_count_reset()
+    barrier()
+    evs = []
+    for _ in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = step()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    launches = native.launch_count()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    # the collective alone: all-reduce of a flat fp32 buffer of the gradients' size
+    ar_ms = None
+    if world > 1:
+        flat = torch.zeros(nparams, dtype=torch.float32, device=dev)
+        for _ in range(3):
+            dist.all_reduce(flat)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            dist.all_reduce(flat)
+        e1.record()
+        torch.cuda.synchronize()
+        ar_ms = e0.elapsed_time(e1) / 10
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        return
+    pairs = world * B * args.steps
+    # forward flops per pair at 384x512 (SURVEY.md Appendix C scaled by the pixel count): 12 x (update block 37.7 + NCUP 6.1)
+    # + encoders 184 GFLOP at 440x1024; backward ~ 2x forward
+    scale = (H * W) / (440.0 * 1024.0)
+    fwd_gflop = (iters * (37.7 + 6.1) + 184.0) * scale
+    print(json.dumps({
+        "mode": "train", "metric": TRAIN_METRIC, "value": pairs / (ms * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cfg5: batch={B}/GPU ({B * world} global) 384x512, 12 iters, {args.model}, sequence loss gamma 0.85, AdamW + "
+                               "OneCycleLR, clip 1.0, train mode with frozen BatchNorm; forward AND backward through librnc's exact fp32 "
+                               "kernels (conv fwd/dgrad/wgrad, corr lookup fwd/bwd, NConv fwd/bwd)",
+                   "parallelism": f"ddp x{world} (one process per GPU, NCCL gradient all-reduce, bucket 8 MB)" if world > 1 else "single GPU",
+                   "timing": "CUDA events per step incl. H2D of the step's inputs, max over ranks"},
+        "loss_last": float(loss), "parameters": nparams, "grad_bytes": nparams * 4,
+        "allreduce": {"alone_ms": ar_ms, "bytes": nparams * 4,
+                      "bus_GBps": (2 * (world - 1) / world * nparams * 4 / (ar_ms * 1e-3) / 1e9) if ar_ms else None,
+                      "note": "all-reduce of a flat fp32 buffer of the gradients' size, 10 back-to-back; inside the step it is "
+                              "bucketed and overlapped with the backward pass"},
+        "tflops_fp32": 3 * fwd_gflop * B * 1e9 / (ms / args.steps * 1e-3) / 1e12,
+        "gpu_launches": int(launches), "clocks": clocks}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -494,6 +593,8 @@ def main():
     ap.add_argument("--model", default="raft_nc_dbl", choices=["raft_nc_dbl", "raft"])
     ap.add_argument("--batch", type=int, default=BATCH, help="pairs per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"], help="train: one optimisation step per timed step (cfg 5)")
+    ap.add_argument("--train-batch", type=int, default=2, help="pairs per GPU in --mode train")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -510,7 +611,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_native(args, rank, world, local_rank)
+        if args.mode == "train":
+            run_train(args, rank, world, local_rank)
+        else:
+            run_native(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist
