@@ -47,6 +47,7 @@ def use_reference_path():
 H_IMG, W_IMG, ITERS, BATCH = 436, 1024, 32, 8
 K2_BYTES_PER_PAIR_ITER = 25_891_840      # fmap1 + coords + out + fmap2 pyramid, fp32
 K4_BYTES_PER_PAIR_CALL = 3_886_080       # flow_lr + conf read, 2x64xP fp32 written
+K4_FMA_PER_PIXEL = 2 * (4 * 2 + 2 * 25 * 2 + 2 * 9 * 2 + 2)    # num + den streams: nconv_in (<= 4 live taps), x2, decoder, out
 K5_BYTES_PER_PAIR_CALL = 19_880_960      # mask 16,220,160 + flow 56,320 + out 3,604,480
 # same formula at the storage width the tensor-core lookup uses: fp16 fmap1/fmap2 pyramid, fp32 coords, 2 x fp16 outputs
 K2_STORAGE_BYTES_PER_PAIR_ITER = 2 * 7040 * 256 + 8 * 7040 + 4 * 7040 * 324 + 2 * 256 * 9280
@@ -451,7 +452,11 @@ def run_native(args, rank, world, local_rank):
                                           "neighbouring kernels)"}},
         "roofline_ncup": {"kernel": "ncup_fused_kernel (K4)", "bound": "hbm", "achieved": k4_gbs, "peak": peak, "unit": "GB/s",
                           "frac": k4_gbs / peak, "avg_launch_ms": k4_ms,
-                          "algorithmic_bytes_per_launch": K4_BYTES_PER_PAIR_CALL * args.batch},
+                          "algorithmic_bytes_per_launch": K4_BYTES_PER_PAIR_CALL * args.batch,
+                          "fma_pipe": {"tflops_fp32": (K4_FMA_PER_PIXEL * 2 * args.batch * 2 * 440 * 1024 / (k4_ms * 1e-3) / 1e12) if k4_ms else None,
+                                       "peak_tflops_fp32": 74.5,
+                                       "note": "the chain is ~300 multiply-adds per output pixel (4 normalized convolutions, num and den "
+                                               "streams): bound by the FP32 FMA pipe (148 SMs x 128 lanes x 2 x 1.965 GHz), not by HBM"}},
         "roofline_convex": {"kernel": "convex_upsample_kernel (K5, model raft)", "bound": "hbm",
                             "achieved": (K5_BYTES_PER_PAIR_CALL * args.batch / (k5_ms * 1e-3) / 1e9) if k5_ms else None, "peak": peak,
                             "unit": "GB/s", "frac": (K5_BYTES_PER_PAIR_CALL * args.batch / (k5_ms * 1e-3) / 1e9 / peak) if k5_ms else None,

@@ -272,6 +272,11 @@ int rnc_flow_x2_fwd(const float* coords1, int B, int H8, int W8, float* x4, void
 int rnc_ncup_guidance_fwd(const float* x_lowres, const float* net, int ldg, int C, int B, int H8, int W8,
                           float* out, int ldo, void* stream);
 
+/* The same staging written directly as split halves planes [B][2*H8][2*W8][ldo] (ldo % 8 == 0, channels >= 2+C zero): the
+ * operand of the tensor-core weights net, without the fp32 intermediate. */
+int rnc_ncup_guidance_split_fwd(const float* x_lowres, const float* net, int ldg, int C, int B, int H8, int W8,
+                                void* out_hi, void* out_lo, int ldo, void* stream);
+
 /* U4 tail: Simple.out (1x1 conv 32->2) + sigmoid (interp_weights_est.py:37,47; upsampler.py:44-46):
  *   in CL [B][H4][W4][cin] -> conf NCHW [B][2][H4][W4]. weight packed [cin][2]. */
 int rnc_conf_head_fwd(const float* in, int cin, int ldi, const float* weight, const float* bias,

@@ -150,6 +150,34 @@ __global__ void ncup_guidance_kernel(const float* __restrict__ x_lowres, const f
   }
 }
 
+// Same staging, written directly as the hi/lo split halves planes the tensor-core weights net consumes (no fp32 round trip):
+// thread = one pixel x 8 channels, one 16-byte store per plane.
+__global__ void ncup_guidance_split_kernel(const float* __restrict__ x_lowres, const float* __restrict__ net, int ldg, int C,
+                                           int B, int H8, int W8, __half* __restrict__ out_hi, __half* __restrict__ out_lo, int ldo) {
+  const int H4 = 2 * H8, W4 = 2 * W8, groups = ldo >> 3;
+  const long long n = static_cast<long long>(B) * H4 * W4 * groups;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % groups);
+    long long r = i / groups;
+    const int x = static_cast<int>(r % W4); r /= W4;
+    const int y = static_cast<int>(r % H4);
+    const int b = static_cast<int>(r / H4);
+    const float* np = net + ((static_cast<size_t>(b) * H8 + (y >> 1)) * W8 + (x >> 1)) * ldg;   // 'area' x2 == replicate
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = 8 * g + j;
+      v[j] = c < 2 ? x_lowres[((static_cast<size_t>(b) * 2 + c) * H4 + y) * W4 + x] : c < 2 + C ? __ldg(np + c - 2) : 0.f;
+    }
+    uint32_t hh[4], ll[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_pair(v[2 * j], v[2 * j + 1], hh[j], ll[j]);
+    const size_t o = ((static_cast<size_t>(b) * H4 + y) * W4 + x) * ldo + 8 * g;
+    *reinterpret_cast<uint4*>(out_hi + o) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+    *reinterpret_cast<uint4*>(out_lo + o) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+  }
+}
+
 // ---------------------------------------------------------------- fp32 CL -> exact hi/lo halves planes
 __global__ void f32_to_split_kernel(const float* __restrict__ src, int lds, int C, long long M, __half* __restrict__ hi,
                                     __half* __restrict__ lo, int ldd, int ch_off) {
@@ -367,6 +395,18 @@ int rnc_ncup_guidance_fwd(const float* x_lowres, const float* net, int ldg, int 
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
   ncup_guidance_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x_lowres, net, ldg, C, B, H8, W8, out, ldo);
+  return after_launch();
+}
+
+int rnc_ncup_guidance_split_fwd(const float* x_lowres, const float* net, int ldg, int C, int B, int H8, int W8,
+                                void* out_hi, void* out_lo, int ldo, void* stream) {
+  if (B <= 0 || H8 <= 0 || W8 <= 0 || C <= 0 || ldg < C || ldo < C + 2 || (ldo & 7)) return RNC_ERR_BAD_SHAPE;
+  if (!x_lowres || !net || !out_hi || !out_lo || !aligned16(out_hi) || !aligned16(out_lo)) return RNC_ERR_BAD_POINTER;
+  const long long n = static_cast<long long>(B) * 4 * H8 * W8 * (ldo >> 3);
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  ncup_guidance_split_kernel<<<static_cast<int>(blocks), 256, 0, as_stream(stream)>>>(
+      x_lowres, net, ldg, C, B, H8, W8, static_cast<__half*>(out_hi), static_cast<__half*>(out_lo), ldo);
   return after_launch();
 }
 

@@ -175,7 +175,6 @@ class UmmaWorkspace:
         if with_ncup:
             M4 = 4 * M
             self.x4 = torch.empty(B, 2, 2 * H8, 2 * W8, **f)
-            self.gin32 = torch.empty(M4, 132, **f)
             self.gin = SplitBuf(M4, GIN_LD, device)
             self.g1 = SplitBuf(M4, 64, device)
             self.g2 = torch.empty(M4, 32, **f)
@@ -380,9 +379,8 @@ class UmmaEngine(Engine):
         M4 = B * H4 * W4
         s = _stream()
         L = self.L
-        native.check(L.rnc_ncup_guidance_fwd(_ptr(x_lowres), C.c_void_p(guid_ptr), ldg, 128, B, H8, W8, _ptr(ws.gin32), 132, s),
-                     "ncup_guidance")
-        native.check(L.rnc_f32_to_split(_ptr(ws.gin32), 132, 132, M4, _ptr(ws.gin.hi), _ptr(ws.gin.lo), GIN_LD, 0, s), "f32_to_split")
+        native.check(L.rnc_ncup_guidance_split_fwd(_ptr(x_lowres), C.c_void_p(guid_ptr), ldg, 128, B, H8, W8, _ptr(ws.gin.hi),
+                                                   _ptr(ws.gin.lo), GIN_LD, s), "ncup_guidance_split")
         self.uconv(B, H4, W4, ws.gin.ptrs(), 132, GIN_LD, pu.u0, native.EPI_RELU, out_split=ws.g1.ptrs(), ldo_split=64)
         self.uconv(B, H4, W4, ws.g1.ptrs(), 64, 64, pu.u1, native.EPI_RELU, out_f32=ws.g2.data_ptr(), ldo_f32=32)
         native.check(L.rnc_conf_head_fwd(_ptr(ws.g2), pu.c_mid1, 32, _ptr(pu.gout[0]), _ptr(pu.gout[1]), B, H4, W4, _ptr(ws.conf), s),

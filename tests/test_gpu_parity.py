@@ -218,11 +218,15 @@ def test_end_to_end_kitti_config_and_warm_start(gold):
     assert epe(lo.cpu(), gold["warm_flow_low"]) < 1e-4 and epe(up.cpu(), gold["warm_flow_up"]) < 1e-3
 
 
-def test_training_mode_is_rejected_on_gpu():
+def test_training_mode_builds_an_autograd_graph():
+    """train mode + grad enabled -> the training path (rnc/train.py): a list of `iters` predictions that back-propagate."""
     m = build_model("raft_nc_dbl").to(DEV).train()
-    im = torch.zeros(1, 3, 128, 256, device=DEV)
-    with pytest.raises(NotImplementedError):
-        m(im, im, iters=1)
+    m.freeze_bn()
+    im1, im2 = frames(1, 128, 160)
+    preds = m(im1.to(DEV), im2.to(DEV), iters=2)
+    assert len(preds) == 2 and preds[-1].requires_grad and preds[-1].shape == (1, 2, 128, 160)
+    preds[-1].abs().mean().backward()
+    assert m.update_block.flow_head.conv2.weight.grad is not None and torch.isfinite(m.fnet.conv1.weight.grad).all()
 
 
 def test_batch_items_are_independent():

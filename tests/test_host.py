@@ -120,11 +120,11 @@ def test_cpu_tensors_fail_loudly_no_fallback():
         CorrBlock(torch.zeros(1, 256, 16, 32), torch.zeros(1, 256, 16, 32))
 
 
-def test_training_mode_is_rejected_loudly():
+def test_training_on_cpu_tensors_fails_loudly_too():
+    from rnc.native import RncUnavailable
     m = build_model("raft_nc_dbl").train()
     im = torch.zeros(1, 3, 128, 256)
-    # (device check comes first for CPU tensors; the grad check is exercised on GPU in test_gpu_parity)
-    with pytest.raises(Exception):
+    with pytest.raises(RncUnavailable):                       # the training path has no CPU fallback either
         m(im, im, iters=1)
 
 
