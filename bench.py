@@ -61,6 +61,7 @@ def ncu_traffic(kernel_key):
             return json.load(f).get(kernel_key, {}).get("dram_bytes_per_launch")
     return None
 METRIC = "image-pairs/sec @ 1024x436, 32 iters"
+TRAIN_METRIC = "training image-pairs/sec @ 512x384, 12 iters (BASELINE configs[4])"
 
 
 def peaks():
@@ -211,6 +212,8 @@ def run_reference_gpu(args):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     dev = torch.device("cuda", 0)
+    if args.mode == "train":
+        return run_reference_gpu_train(args, dev)
     model = reference_model(args.model).to(dev)
     p1, p2 = synth_frames(args.batch, 7)
     d1, d2 = p1.to(dev), p2.to(dev)
@@ -232,12 +235,46 @@ def run_reference_gpu(args):
                               "inputs resident, CUDA events"}))
 
 
+def run_reference_gpu_train(args, dev):
+    """The reference's own training step in eager PyTorch on the GPU (train.py:203-227 without AMP): unmodified modules from
+    baseline/_ref, train mode + freeze_bn, sequence loss (train.py:46-71 restated: train.py itself does not import), AdamW,
+    clip 1.0 — the comparator of `--mode train`."""
+    B, H, W, iters = args.train_batch, 384, 512, 12
+    model = reference_model(args.model).to(dev).train()
+    model.freeze_bn()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=5e-5, eps=1e-8)
+    g = torch.Generator().manual_seed(100)
+    im1, im2 = (torch.rand(B, 3, H, W, generator=g) * 255).to(dev), (torch.rand(B, 3, H, W, generator=g) * 255).to(dev)
+    gt, valid = (torch.randn(B, 2, H, W, generator=g) * 5).to(dev), torch.ones(B, H, W, device=dev)
+    times = []
+    for i in range(3 + args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        opt.zero_grad()
+        preds = model(im1, im2, iters=iters)
+        mag = torch.sum(gt ** 2, dim=1).sqrt()
+        val = (valid >= 0.5) & (mag < 400)
+        loss = sum(0.85 ** (len(preds) - k - 1) * (val[:, None] * (p - gt).abs()).mean() for k, p in enumerate(preds))
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            times.append(e0.elapsed_time(e1))
+    ms = sum(times) / len(times)
+    print(json.dumps({"impl": "reference_gpu", "mode": "train", "metric": TRAIN_METRIC, "value": B / (ms * 1e-3), "unit": "pairs/s",
+                      "ms_per_step": ms, "steps": args.steps, "batch": B, "model": args.model, "dtype": "f32", "tf32": False,
+                      "loss_last": float(loss),
+                      "note": "unmodified reference modules (baseline/_ref) in eager PyTorch, cuDNN/cuBLAS TF32 disabled"}))
+
+
 def gpu_eager_baseline(args):
     """Run the reference_gpu leg in a fresh process (module names `raft_nc_dbl`, `update`, `corr`, ... clash with the drop-in)."""
     if not os.path.isdir(REF_CORE):
         return {"unavailable": "baseline/_ref not installed (run baseline/install_reference.sh)"}
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference_gpu", "--steps", "2", "--warmup", "1",
-           "--batch", str(args.batch), "--model", args.model]
+           "--batch", str(args.batch), "--model", args.model, "--mode", args.mode, "--train-batch", str(args.train_batch)]
     try:
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=900,
                              env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
@@ -490,9 +527,6 @@ def cpu_baseline_subprocess(args):
         return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
-TRAIN_METRIC = "training image-pairs/sec @ 512x384, 12 iters (BASELINE configs[4])"
-
-
 def run_train(args, rank, world, local_rank):
     """BASELINE configs[4] / SURVEY.md §8e: one optimisation step of raft_nc_dbl per timed step — batch 2 per GPU (16 on 8 GPUs),
     384x512 synthetic frames, 12 iterations, sequence loss, AdamW + OneCycle, gradient clipping; under torchrun the replicas are
@@ -586,7 +620,8 @@ def run_train(args, rank, world, local_rank):
                       "note": "all-reduce of a flat fp32 buffer of the gradients' size, 10 back-to-back; inside the step it is "
                               "bucketed and overlapped with the backward pass"},
         "tflops_fp32": 3 * fwd_gflop * B * 1e9 / (ms / args.steps * 1e-3) / 1e12,
-        "gpu_launches": int(launches), "clocks": clocks}))
+        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_eager_baseline": gpu_eager_baseline(args) if world == 1 and not args.no_cpu_baseline else None}))
 
 
 def main():
