@@ -281,12 +281,16 @@ class Engine:
     """Issues the kernels.  One per CUDA device (engine_for); keeps packed weights and workspaces.  ``lock`` serialises the
     forwards of one device (nn.DataParallel drives different devices from different threads: different engines)."""
     mode = "ffma"
+    fork_convf1 = False
     PACK_UB, PACK_UP = PackedUpdateBlock, PackedUpsampler
     WS = Workspace
     MAX_WS, MAX_PACKED = 6, 64
 
+    MAX_GRAPHS = 4
+
     def __init__(self):
         self.profile = None
+        self._graphs = OrderedDict()        # forward signature -> captured CUDA graph (test-mode inference), LRU
         self._packed = OrderedDict()        # (kind, param key) -> packed weights, LRU
         self._ws = OrderedDict()            # workspace key -> workspace, LRU
         self.lock = threading.RLock()
@@ -323,6 +327,58 @@ class Engine:
         else:
             self._ws.move_to_end(key)
         return ws
+
+    # ------------------------------------------------------------------ whole-forward CUDA graphs (test-mode inference)
+    def graphs_enabled(self, model):
+        """A test-mode forward issues ~560 kernels; replaying them as one CUDA graph removes the host launch path (matters for
+        single pairs, evaluate.py's usage, and for eight ranks sharing a host).  Off while bench.py brackets kernels with events
+        (profile), for nn.DataParallel replicas (fresh weight copies every call) and with RNC_GRAPH=0."""
+        if self.profile is not None or os.environ.get("RNC_GRAPH", "1") == "0":
+            return False
+        if os.environ.get("RNC_PARAM_CHECK", "") == "checksum" or getattr(model, "_is_replica", False):
+            return False
+        return not getattr(model.args, "mixed_precision", False) and os.environ.get("RNC_ENCODER", "umma").lower() == "umma" \
+            and self.mode == "umma" and not self.fork_convf1
+
+    def graph_forward(self, model, image1, image2, iters, flow_init):
+        """Second and later forwards with the same signature (shape, iterations, warm start or not, weights) replay a captured
+        graph: inputs are copied into the graph's static buffers, results are returned as fresh copies."""
+        B, _, Him, Wim = image1.shape
+        if flow_init is not None and tuple(flow_init.shape) != (B, 2, Him // 8, Wim // 8):
+            raise ValueError("flow_init must be [N,2,H/8,W/8]")
+        key = (type(model).__name__, tuple(image1.shape), iters, flow_init is not None, _param_key(model))
+        ent = self._graphs.get(key)
+        if ent is None:
+            while len(self._graphs) >= self.MAX_GRAPHS:
+                self._graphs.popitem(last=False)
+            self._graphs[key] = {"seen": 1}
+            return model._forward_eager(self, image1, image2, iters, flow_init, True)     # first sight: eager (also warms caches)
+        self._graphs.move_to_end(key)
+        if "graph" not in ent:
+            ent["im1"], ent["im2"] = image1.detach().float().clone(), image2.detach().float().clone()
+            ent["fi"] = flow_init.detach().float().clone() if flow_init is not None else None
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream(device=image1.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):                                                  # warm-up on a side stream
+                model._forward_eager(self, ent["im1"], ent["im2"], iters, ent["fi"], True)
+            cur.wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                ent["out"] = model._forward_eager(self, ent["im1"], ent["im2"], iters, ent["fi"], True)
+                ent["net"] = model.update_block.net
+            ent["graph"] = g
+            # the graph addresses these buffers by pointer: keep them alive even if the LRU caches let go of them
+            enc = getattr(self, "_encoder", None)
+            ent["pins"] = (dict(self._ws), dict(self._packed), enc._bufs if enc is not None else None)
+        ent["im1"].copy_(image1)
+        ent["im2"].copy_(image2)
+        if ent["fi"] is not None:
+            ent["fi"].copy_(flow_init)
+        ent["graph"].replay()
+        model.update_block.net = ent["net"]
+        lo, up = ent["out"]
+        return lo.clone(), up.clone()
 
     # ------------------------------------------------------------------ single kernels
     def conv(self, B, H, W, in0, c0, ld0, packed, cout, kh, kw, epi, out=None, ldo=0, in1=None, c1=0, ld1=0,

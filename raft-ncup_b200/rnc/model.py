@@ -81,6 +81,12 @@ class _RAFTBase(nn.Module):
         B, _, Him, Wim = image1.shape
         if Him % 8 or Wim % 8:
             raise ValueError("image height/width must be multiples of 8 (pad with utils.utils.InputPadder, evaluate.py:125)")
+        if test_mode and eng.graphs_enabled(self):
+            return eng.graph_forward(self, image1, image2, iters, flow_init)
+        return self._forward_eager(eng, image1, image2, iters, flow_init, test_mode)
+
+    def _forward_eager(self, eng, image1, image2, iters, flow_init, test_mode):
+        B, _, Him, Wim = image1.shape
         H8, W8 = Him // 8, Wim // 8
         L = eng.L
         pk = eng.packed_update(self.update_block)
