@@ -24,8 +24,9 @@ namespace rnc {
 constexpr int NT = 30;             // output tile side
 constexpr int R1 = NT + 6;         // stage-1 region side (halo 3) = 36
 constexpr int R2 = NT + 2;         // stage-2 region side (halo 1) = 32
-constexpr int P1 = R1;             // stage-1 row pitch (float2): a 1x4 item reads columns [4g, 4g + 8) <= 36; 288-byte rows
-constexpr int P2 = R2;             // stage-2 row pitch (float2): a 1x2 item reads columns [2g, 2g + 4) <= 32; 256-byte rows
+constexpr int P1 = R1 + 2;         // stage-1 row pitch (float2): a 1x4 item reads columns [4g, 4g + 8) <= 36; 304-byte rows
+constexpr int P2 = R2 + 2;         // stage-2 row pitch (float2): 272-byte rows — a 256-byte pitch would put the four rows a warp
+                                   // stores at once into the same banks (ncu: LSU data pipe 76 % busy, ahead of the FMA pipe)
 constexpr int LT = 12;             // lattice samples per side
 constexpr float kEps = 1e-20f;     // nconv_modules.py:149
 
@@ -126,11 +127,17 @@ ncup_fused_kernel(const float* __restrict__ x_lowres, const float* __restrict__ 
       }
     const int y = ty0 - 1 + ry;
 #pragma unroll
-    for (int x = 0; x < 4; ++x) {
-      const int xx = tx0 - 1 + 4 * g + x;
-      const bool in = y >= 0 && y < H && xx >= 0 && xx < W;
-      s2[0][ry][4 * g + x] = in ? nconv_out_pair(acc[x][0], w.inv_s2[0]) : make_float2(0.f, 0.f);
-      s2[1][ry][4 * g + x] = in ? nconv_out_pair(acc[x][1], w.inv_s2[1]) : make_float2(0.f, 0.f);
+    for (int x = 0; x < 4; x += 2) {           // two positions = one 16-byte store per channel
+      float2 o[2][2];
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        const int xx = tx0 - 1 + 4 * g + x + d;
+        const bool in = y >= 0 && y < H && xx >= 0 && xx < W;
+        o[d][0] = in ? nconv_out_pair(acc[x + d][0], w.inv_s2[0]) : make_float2(0.f, 0.f);
+        o[d][1] = in ? nconv_out_pair(acc[x + d][1], w.inv_s2[1]) : make_float2(0.f, 0.f);
+      }
+      *reinterpret_cast<float4*>(&s2[0][ry][4 * g + x]) = make_float4(o[0][0].x, o[0][0].y, o[1][0].x, o[1][0].y);
+      *reinterpret_cast<float4*>(&s2[1][ry][4 * g + x]) = make_float4(o[0][1].x, o[0][1].y, o[1][1].x, o[1][1].y);
     }
   }
   __syncthreads();

@@ -46,7 +46,7 @@ class UmmaWeights:
     """[Cout,Cin,KH,KW] -> hi/lo halves planes [CoutPad][taps * blocks * 64] scaled by 2^s (s chosen so the largest
     weight lands in [512, 1024): w_lo then stays a normal half) + fp32 bias [CoutPad] + unscale = 2^-s."""
 
-    def __init__(self, weight, bias, segs, extra_cout=0, out_scale=1.0):
+    def __init__(self, weight, bias, segs, extra_cout=0, out_scale=1.0, scale_log2=None):
         cout, cin, kh, kw = weight.shape
         w = weight.detach().float() * out_scale
         nblks = [(c + 63) // 64 for c in segs]
@@ -63,8 +63,11 @@ class UmmaWeights:
             ci += take
             col += nb * 64
         assert ci == cin, "segments do not cover the weight's input channels"
-        mx = float(wp.abs().max())
-        s = math.floor(math.log2(1000.0 / mx)) if mx > 0 else 0
+        if scale_log2 is None:
+            mx = float(wp.abs().max())                       # (one device sync; inference packs once per checkpoint)
+            s = math.floor(math.log2(1000.0 / mx)) if mx > 0 else 0
+        else:
+            s = scale_log2                                   # training re-packs every step: fixed scale, no sync (|w| < 2^(15-s))
         ws = wp.reshape(self.coutpad, self.ktot) * (2.0 ** s)
         self.w_hi = ws.half().contiguous()
         self.w_lo = (ws - self.w_hi.float()).half().contiguous()

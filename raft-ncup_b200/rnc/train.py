@@ -47,6 +47,66 @@ def _ceil4(c):
     return (c + 3) // 4 * 4
 
 
+def _umma_ok(eng, Cx, cout):
+    """The tensor-core convolution (fp16 hi/lo split operands, fp32-faithful: 3 MMAs per K step) serves a training-path layer when
+    its operand pitch is a multiple of 8 halves and its fp32 output row needs no wider padding than the channel-last tensors use
+    (the kernel stores whole 32-channel chunks).  Thin layers (flow, image, 2-channel heads) stay on the exact CUDA-core kernel."""
+    import os
+    if eng.mode != "umma" or os.environ.get("RNC_TRAIN_CONV", "umma") != "umma":
+        return False
+    return Cx % 8 == 0 and Cx >= 32 and cout >= 32 and (cout + 31) // 32 * 32 == _ceil4(cout)
+
+
+def _packed_umma(weight, kind, cin_pad):
+    from .engine_umma import UmmaWeights
+    key = (id(weight), weight._version, kind + "_umma", cin_pad)
+    hit = _PACK_CACHE.get(key)
+    if hit is None or hit[0] is not weight:
+        w = weight.detach().float()
+        if kind == "dgrad":
+            w = w.flip(2, 3).transpose(0, 1)
+        if w.shape[1] != cin_pad:
+            w = F.pad(w, (0, 0, 0, 0, 0, cin_pad - w.shape[1]))
+        # fixed scale 2^10 (no device sync per pack): exact for |w| < 32; a lo part below the half normal range only costs an
+        # absolute 2^-34 per weight
+        hit = _PACK_CACHE[key] = (weight, UmmaWeights(w.contiguous(), None, [cin_pad], scale_log2=10))
+    return hit[1]
+
+
+def _conv_launch_umma(eng, x, wt, cout, stride=1, bias=None):
+    """Same contract as _conv_launch on the tcgen05 path: x fp32 CL -> split halves (rnc_f32_to_split) -> rnc_conv2d_umma_fwd with
+    an fp32 channel-last output; stride 2 is native (TMA element strides), no subsampling pass."""
+    from .engine_umma import SplitBuf
+    B, H, W, Cx = x.shape
+    Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
+    M = B * H * W
+    xs = SplitBuf.__new__(SplitBuf)
+    xs.hi = torch.empty(M, Cx, dtype=torch.float16, device=x.device)
+    xs.lo = torch.empty(M, Cx, dtype=torch.float16, device=x.device)
+    xs.ld = Cx
+    native.check(eng.L.rnc_f32_to_split(_ptr(x), Cx, Cx, M, _ptr(xs.hi), _ptr(xs.lo), Cx, 0, _stream()), "f32_to_split")
+    ldo = _ceil4(cout)
+    out = torch.empty(B, Ho, Wo, ldo, dtype=torch.float32, device=x.device)
+    if bias is not None:
+        wt = _with_bias(wt, bias)
+    eng.uconv(B, Ho, Wo, xs.ptrs(), Cx, Cx, wt, native.EPI_LINEAR, out_f32=out.data_ptr(), ldo_f32=ldo, stride=stride, hin=H, win=W)
+    return out
+
+
+class _WithBias:
+    """A packed weight with this call's bias vector (the pack is cached per weight; biases are tiny and change with it)."""
+
+    def __init__(self, wt, bias):
+        self.__dict__.update(wt.__dict__)
+        b = torch.zeros_like(wt.bias)
+        b[:wt.cout] = bias.detach()
+        self.bias = b
+
+
+def _with_bias(wt, bias):
+    return _WithBias(wt, bias)
+
+
 def _conv_launch(eng, x, packed, cout, kh, kw, bias=None):
     """x CL [B,H,W,C] contiguous (C % 4 == 0) -> CL [B,H,W,ceil4(cout)] (pad channels zero), stride 1, zero padding k/2."""
     B, H, W, Cx = x.shape
@@ -80,11 +140,14 @@ class ConvCL(torch.autograd.Function):
         Cx = x.shape[-1]
         if Cx % 4 or Cx < cin:
             raise ValueError("ConvCL: input must be channel-last with ceil4(Cin) channels")
-        y = _conv_launch(eng, x, _packed(weight, "fwd", Cx), cout, kh, kw, bias)
-        if stride == 2:
-            y = y[:, ::2, ::2].contiguous()          # same padding: out(y, x) of the strided conv = full(2y, 2x)
-        elif stride != 1:
+        if stride not in (1, 2):
             raise NotImplementedError("stride 1 or 2")
+        if _umma_ok(eng, Cx, cout):
+            y = _conv_launch_umma(eng, x, _packed_umma(weight, "fwd", Cx), cout, stride, bias)
+        else:
+            y = _conv_launch(eng, x, _packed(weight, "fwd", Cx), cout, kh, kw, bias)
+            if stride == 2:
+                y = y[:, ::2, ::2].contiguous()      # same padding: out(y, x) of the strided conv = full(2y, 2x)
         ctx.save_for_backward(x, weight)
         ctx.stride, ctx.has_bias = stride, bias is not None
         return y
@@ -104,7 +167,10 @@ class ConvCL(torch.autograd.Function):
                 if ctx.stride == 2:
                     g_full = torch.zeros(B, H, W, ldg, dtype=torch.float32, device=x.device)
                     g_full[:, ::2, ::2] = gy
-                gx = _conv_launch(eng, g_full, _packed(weight, "dgrad", ldg), cin, kh, kw)
+                if _umma_ok(eng, ldg, cin):
+                    gx = _conv_launch_umma(eng, g_full, _packed_umma(weight, "dgrad", ldg), cin)
+                else:
+                    gx = _conv_launch(eng, g_full, _packed(weight, "dgrad", ldg), cin, kh, kw)
                 if gx.shape[-1] != Cx:               # Cx > ceil4(cin) never happens; equal by construction
                     gx = F.pad(gx, (0, Cx - gx.shape[-1]))
             if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
@@ -355,7 +421,7 @@ def ncup_upsampler_train(up, x_lowres, x_guidance, out_scale=1.0):
     _require_cuda(x_lowres, x_guidance)
     with torch.cuda.device(x_lowres.device):
         g4 = F.interpolate(x_guidance, x_lowres.shape[2:], mode="area")           # integer x2 'area' upscale = replication
-        w4 = simple_cl(up.weights_est_net, to_cl(torch.cat([x_lowres, g4], 1)))
+        w4 = simple_cl(up.weights_est_net, to_cl(torch.cat([x_lowres, g4], 1), pad_to=136))     # pitch % 8 == 0: tensor-core layer
         xh, wh = zero_stuff(x_lowres), zero_stuff(w4)
         b, c, oh, ow = xh.shape
         out, _ = nconv_unet_train(up.interpolation_net, xh.view(b * c, 1, oh, ow), wh.view(b * c, 1, oh, ow))
