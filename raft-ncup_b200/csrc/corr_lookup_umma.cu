@@ -42,8 +42,17 @@ namespace lookup_umma {
 
 using namespace rnc::umma;
 
-// One epilogue warp per TMEM lane group.
-constexpr int kEpiWarps = 4;
+// RNC_LOOKUP_EPI2=1 (compile-time variant): TWO epilogue warps per TMEM lane group share every accumulator chunk — the rows a
+// chunk holds for the lane group are cut in half, the halves alternate between the two warps from chunk to chunk (so each warp's
+// rows are consecutive across a chunk boundary and its y-blend state carries over; the warp taking a second half re-derives the
+// x-interpolated row in front of it), one box row per step with a one-row scratch each.  Bit-identical results; measured on
+// B200 at B=8: 67.1 us per launch against 67.0 us for the default one-warp form (two rows per step) — after the round-2 rework
+// the kernel is bound by its TMA feed (loads alone ~40 us, loads + MMA ~54 us), not by the epilogue any more, so the default
+// stays the simpler form.
+#ifndef RNC_LOOKUP_EPI2
+#define RNC_LOOKUP_EPI2 0
+#endif
+constexpr int kEpiWarps = RNC_LOOKUP_EPI2 ? 8 : 4;
 constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA + TMEM, then the epilogue warps
 constexpr int kTY = 8, kTX = 16;         // query tile (level-0 pixels)
 constexpr int kD = 256;                  // feature channels
@@ -90,9 +99,9 @@ constexpr int kSmemB = kStages * kBStage;                    // 64 KB
 // scratch [pixel][68] words: two box rows (32 words each); the pixels of the odd tile row of a warp are skewed by 16 words, so
 // that the gather's scalar loads (lane address = 68*pixel + skew + window offset, window offset ~ pixel's x) hit 32 distinct
 // banks: bank = 5*lane + spread (mod 32)
-constexpr int kScrStride = 68, kScrSkew = 16;
+constexpr int kScrStride = RNC_LOOKUP_EPI2 ? 36 : 68, kScrSkew = 16;   // one (EPI2) or two box rows of 32 words + 4: 36 = 68 = 4 (mod 32)
 constexpr int kScrWarp = 32 * kScrStride + kScrSkew;         // words per epilogue warp (its 16 skewed pixels run 16 words past 32*68)
-constexpr int kSmemScratch = 4 * kScrWarp * 4;               // 34.25 KB
+constexpr int kSmemScratch = kEpiWarps * kScrWarp * 4;       // 34.25 KB (4 warps x two rows) / 36.5 KB (8 warps x one row)
 // output tile of one (tile, level) unit: [plane hi | lo][128 px][88 halves], dense = the TMA store's box {88, 16, 2} per warp
 constexpr int kStgPlane = 128 * kLvlStride * 2;              // 22 KB
 constexpr int kSmemStage = 2 * kStgPlane;                    // 44 KB
@@ -134,6 +143,7 @@ __device__ __forceinline__ float clamp_coord(float v) { return fminf(fmaxf(v, -1
 struct EpiCtx {
   const Params& p; const TileInfo* ti; float* scratch; __half* stage; uint64_t* acc_full; uint64_t* acc_empty;
   uint32_t tmem_base; int b, y0, x0, lg, ml, lane; bool valid; float cx, cy;
+  int team;                            // EPI2: 0 / 1 = first / second epilogue warp of the lane group
 };
 
 template <int BW>
@@ -244,6 +254,86 @@ __device__ __forceinline__ void lookup_level_rows(const EpiCtx& c, int& ch, int 
   }
 }
 
+#if RNC_LOOKUP_EPI2
+// Rows of one level for one of the lane group's two warps (see RNC_LOOKUP_EPI2 above): one box row per step.
+template <int BW>
+__device__ __forceinline__ void lookup_level_rows2(const EpiCtx& c, int& ch, int l, bool live, int ox, int oy, float ax, float ay) {
+  const Params& p = c.p;
+  const int cr = chunk_rows(l);
+  float* sc = c.scratch + (c.team * 4 + c.lg) * kScrWarp + c.lane * kScrStride + (c.lane >> 4) * kScrSkew;   // one box row of 32 words
+  __half* sth = c.stage + c.ml * kLvlStride;
+  __half* stl = sth + 128 * kLvlStride;
+  auto emit = [&](int j, const float (&o)[kS]) {
+    uint32_t hh[4], ll[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) split_pair(o[2 * q], o[2 * q + 1], hh[q], ll[q]);
+    *reinterpret_cast<uint4*>(sth + j * 8) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+    *reinterpret_cast<uint4*>(stl + j * 8) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+    uint32_t h8, l8;
+    split_pair(o[8], 0.f, h8, l8);
+    reinterpret_cast<unsigned short*>(sth)[72 + j] = static_cast<unsigned short>(h8 & 0xffffu);
+    reinterpret_cast<unsigned short*>(stl)[72 + j] = static_cast<unsigned short>(l8 & 0xffffu);
+  };
+  const float wx1 = ax * p.scale, wx0 = p.scale - wx1, wy0 = 1.f - ay;
+  const int row_lo = __reduce_min_sync(0xffffffffu, live ? oy : 0x7fffffff);
+  const int row_hi = __reduce_max_sync(0xffffffffu, live ? oy + kG - 1 : -1);
+  float hprev[kS];
+#pragma unroll
+  for (int i = 0; i < kS; ++i) hprev[i] = 0.f;
+  const float* gp = sc + (live ? ox : 0);
+  // one box row: x-interpolate; unless it only primes the y-blend state, blend with the previous row and store window row cidx-1
+  auto step = [&](const uint32_t* v, int row, bool prime) {
+#pragma unroll
+    for (int g4 = 0; g4 < BW / 4; ++g4)
+      *reinterpret_cast<uint4*>(sc + 4 * g4) = make_uint4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+    const int cidx = row - oy;
+    float g[kG], h[kS];
+#pragma unroll
+    for (int a = 0; a < kG; ++a) g[a] = gp[a];
+#pragma unroll
+    for (int i = 0; i < kS; ++i) h[i] = wx0 * g[i] + wx1 * g[i + 1];
+    if (!prime && live && cidx >= 1 && cidx < kG) {
+      float o[kS];
+#pragma unroll
+      for (int i = 0; i < kS; ++i) o[i] = wy0 * hprev[i] + ay * h[i];
+      emit(cidx - 1, o);
+    }
+#pragma unroll
+    for (int i = 0; i < kS; ++i) hprev[i] = h[i];
+  };
+
+  const int nch = (c.ti->nrows + cr - 1) / cr;
+  for (int cc = 0; cc < nch; ++cc, ++ch) {
+    const int buf = ch & 1, use = ch >> 1;
+    mbar_wait(&c.acc_full[buf], use & 1);
+    tcgen05_fence_after();
+    const int r0 = max(0, row_lo - cc * cr), r1 = min(cr - 1, row_hi - cc * cr);   // rows of this chunk the lane group needs
+    const uint32_t tbase = c.tmem_base + (static_cast<uint32_t>(c.lg * 32) << 16) + buf * 256;
+    if (r0 <= r1) {
+      // halves alternate between the two warps: role 0 = first half (continues this warp's rows of the previous chunk),
+      // role 1 = second half (re-derives the row in front of it to prime hprev)
+      const int role = (cc & 1) ^ c.team, nfirst = (r1 - r0 + 2) >> 1;
+      const int a = role == 0 ? r0 : r0 + nfirst - 1, b = role == 0 ? r0 + nfirst - 1 : r1;   // role 1 starts on its priming row
+      uint32_t va[32] = {}, vb[32] = {};
+      tmem_row_issue<BW>(tbase + a * BW, va);
+      for (int r = a; r <= b; r += 2) {
+        tmem_ld_wait32(va);
+        if (r + 1 <= b) tmem_row_issue<BW>(tbase + (r + 1) * BW, vb);
+        step(va, cc * cr + r, role == 1 && r == a);
+        if (r + 1 <= b) {
+          tmem_ld_wait32(vb);
+          if (r + 2 <= b) tmem_row_issue<BW>(tbase + (r + 2) * BW, va);
+          step(vb, cc * cr + r + 1, false);
+        }
+      }
+    }
+    tcgen05_fence_before();
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(&c.acc_empty[buf]);
+  }
+}
+#endif
+
 // Epilogue of one warp (thread = pixel = TMEM lane) for one unit = (tile, level l): rows into the output tile, then one TMA
 // store per plane of the warp's 2 x 16 pixels (the TMA unit clips pixels beyond the image).
 __device__ __forceinline__ void lookup_epilogue(const EpiCtx& c, int& ch, int l, const CUtensorMap* map_hi, const CUtensorMap* map_lo) {
@@ -257,11 +347,16 @@ __device__ __forceinline__ void lookup_epilogue(const EpiCtx& c, int& ch, int l,
   const bool empty = !window_origin(c.cx, c.cy, inv, p.H >> l, p.W >> l, ix0, iy0);
   const int ox = ix0 - c.ti->bx0, oy = iy0 - c.ti->by0;
   const bool live = c.valid && !empty;
-  // the previous unit's TMA stores have finished READING this warp's rows of the output tile
+  // the previous unit's TMA stores have finished READING this lane group's rows of the output tile
+#if RNC_LOOKUP_EPI2
+  if (c.team == 0 && c.lane == 0) bulk_wait_read0();
+  named_bar_sync(1 + c.lg, 64);                // both warps of the lane group: the tile may be rewritten
+#else
   if (c.lane == 0) bulk_wait_read0();
   __syncwarp();
+#endif
 #ifndef RNC_PROBE_NOEPI
-  if (!live) {                                 // window fully outside the level image (or pixel outside the frame): zeros
+  if (!live && (!RNC_LOOKUP_EPI2 || c.team == 0)) {   // window fully outside the level image (or pixel outside the frame): zeros
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
     for (int q = 0; q < 10; ++q) {
@@ -272,14 +367,25 @@ __device__ __forceinline__ void lookup_epilogue(const EpiCtx& c, int& ch, int l,
     reinterpret_cast<unsigned short*>(stl)[80] = 0;
   }
 #endif
+#if RNC_LOOKUP_EPI2
+  if (l == 0) lookup_level_rows2<box_w(0)>(c, ch, l, live, ox, oy, ax, ay);
+  else if (l == 1) lookup_level_rows2<box_w(1)>(c, ch, l, live, ox, oy, ax, ay);
+  else lookup_level_rows2<box_w(2)>(c, ch, l, live, ox, oy, ax, ay);
+#else
   if (l == 0) lookup_level_rows<box_w(0)>(c, ch, l, live, ox, oy, ax, ay);
   else if (l == 1) lookup_level_rows<box_w(1)>(c, ch, l, live, ox, oy, ax, ay);
   else lookup_level_rows<box_w(2)>(c, ch, l, live, ox, oy, ax, ay);
+#endif
   static_assert(box_w(2) == box_w(3), "levels 2 and 3 share the row code");
 #ifndef RNC_PROBE_NOEPI
   fence_proxy_async();                         // this thread's shared-memory writes are visible to the TMA unit
+#if RNC_LOOKUP_EPI2
+  named_bar_sync(1 + c.lg, 64);                // both warps' window rows are in the tile
+  if (c.team == 0 && c.lane == 0) {
+#else
   __syncwarp();
   if (c.lane == 0) {
+#endif
     const __half* src = c.stage + c.lg * 32 * kLvlStride;
     tma_store_4d(map_hi, src, l * kLvlStride, c.x0, c.y0 + 2 * c.lg, c.b);
     tma_store_4d(map_lo, src + 128 * kLvlStride, l * kLvlStride, c.x0, c.y0 + 2 * c.lg, c.b);
@@ -660,6 +766,7 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
     // ------------------------------------------------------------------ epilogue: gather + bilinear blend + store
     // thread = pixel = TMEM lane
     const int lg = warp & 3, ml = lg * 32 + lane;
+    const int team = RNC_LOOKUP_EPI2 ? (warp - 2) >> 2 : 0;
     auto load_coord = [&](int tile, float& ox, float& oy, bool& v) {
       const int b = tile / tpi, tr = tile - b * tpi;
       const int py = (tr / p.tiles_x) * kTY + (ml >> 4), px = (tr % p.tiles_x) * kTX + (ml & 15);
@@ -670,7 +777,7 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
     float cx = 0.f, cy = 0.f, ncx = 0.f, ncy = 0.f;
     bool valid = false, nvalid = false;
 #ifndef RNC_PROBE_NOEPI
-    {                                          // the 7 pad channels of this pixel's output rows stay zero for the whole kernel
+    if (team == 0) {                           // the 7 pad channels of this pixel's output rows stay zero for the whole kernel
       const uint4 z = make_uint4(0u, 0u, 0u, 0u);
       *reinterpret_cast<uint4*>(stage + ml * kLvlStride + 80) = z;
       *reinterpret_cast<uint4*>(stage + (128 + ml) * kLvlStride + 80) = z;
@@ -691,14 +798,14 @@ corr_lookup_umma_kernel(const __grid_constant__ CUtensorMap mF1, const __grid_co
       const int slot = n & (kTiRing - 1);
       mbar_wait(&ti_full[slot], (n >> kTiShift) & 1);
       if (!ti[slot].overflow) {
-        EpiCtx c{p, &ti[slot], scratch, stage, acc_full, acc_empty, tmem_base, b, y0, x0, lg, ml, lane, valid, cx, cy};
+        EpiCtx c{p, &ti[slot], scratch, stage, acc_full, acc_empty, tmem_base, b, y0, x0, lg, ml, lane, valid, cx, cy, team};
         lookup_epilogue(c, ch, l, &mOutHi, &mOutLo);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&ti_empty[slot]);
       ++n;
     }
-    if (lane == 0) bulk_wait_all0();           // the output tile must outlive its TMA stores
+    if (lane == 0 && team == 0) bulk_wait_all0();   // the output tile must outlive its TMA stores
   }
 
   tcgen05_fence_before();

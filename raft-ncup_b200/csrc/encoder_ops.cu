@@ -18,7 +18,10 @@ constexpr int ST_PW = ST_IN_W + 1;                   // patch row pitch
 constexpr int ST_SMEM = (3 * ST_IN_H * ST_PW + 147 * 64) * 4;   // 17.6 KB patch + 37.6 KB weights (dynamic: > 48 KB)
 
 // weight layout [147 = (c*7+ky)*7+kx][64].  Thread = (4 horizontally adjacent output pixels, 16-channel group): per
-// (channel, filter row) the 13 input values of the quad are loaded once and every weight float4 feeds 16 FMAs.
+// (channel, filter row) the 13 input values of the quad are loaded once and every weight float4 feeds 16 multiply-adds, issued
+// as 8 packed FFMA2 (fma.rn.f32x2: two adjacent output channels per instruction) — the kernel is FMA-issue-bound.  In shared
+// memory a tap's 64 weights are stored as [quad q][channel group cg][4], so that the four channel groups of a quarter warp
+// read four consecutive 16-byte chunks (the plain [64] order put groups 0/2 and 1/3 into the same banks).
 __global__ void __launch_bounds__(256)
 stem_conv7x7s2_kernel(const float* __restrict__ img, const float* __restrict__ weight, const float* __restrict__ bias,
                       int N, int Hin, int Win, int Ho, int Wo, int relu, float* __restrict__ out_f32,
@@ -28,7 +31,10 @@ stem_conv7x7s2_kernel(const float* __restrict__ img, const float* __restrict__ w
   float* patch = st_smem + 147 * 64;                   // [3][ST_IN_H][ST_PW]
   const int n = blockIdx.z, oy0 = blockIdx.y * ST_TY, ox0 = blockIdx.x * ST_TX;
   const int tid = threadIdx.x;
-  for (int i = tid; i < 147 * 64 / 4; i += 256) reinterpret_cast<float4*>(wsm)[i] = reinterpret_cast<const float4*>(weight)[i];
+  for (int i = tid; i < 147 * 64 / 4; i += 256) {                // float4 index i = tap*16 + cg*4 + q  ->  tap*16 + q*4 + cg
+    const int tap = i >> 4, cgq = i & 15;
+    reinterpret_cast<float4*>(wsm)[tap * 16 + (cgq & 3) * 4 + (cgq >> 2)] = reinterpret_cast<const float4*>(weight)[i];
+  }
   const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
   for (int i = tid; i < 3 * ST_IN_H * ST_IN_W; i += 256) {
     const int c = i / (ST_IN_H * ST_IN_W), r = i % (ST_IN_H * ST_IN_W);
@@ -41,35 +47,38 @@ stem_conv7x7s2_kernel(const float* __restrict__ img, const float* __restrict__ w
   __syncthreads();
   const int cg = tid & 3, quad = tid >> 2;
   const int ty = quad / (ST_TX / 4), tx = (quad % (ST_TX / 4)) * 4;
-  float acc[4][16];
+  float2 acc2[4][8];                                   // [pixel][channel pair]
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float bv = bias[cg * 16 + j];
-    acc[0][j] = bv; acc[1][j] = bv; acc[2][j] = bv; acc[3][j] = bv;
+  for (int j = 0; j < 8; ++j) {
+    const float2 bv = make_float2(bias[cg * 16 + 2 * j], bias[cg * 16 + 2 * j + 1]);
+    acc2[0][j] = bv; acc2[1][j] = bv; acc2[2][j] = bv; acc2[3][j] = bv;
   }
   for (int c = 0; c < 3; ++c)
     for (int ky = 0; ky < 7; ++ky) {
       const float* prow = &patch[(c * ST_IN_H + ty * 2 + ky) * ST_PW + tx * 2];
-      float a[13];
+      float2 a[13];
 #pragma unroll
-      for (int i = 0; i < 13; ++i) a[i] = prow[i];
+      for (int i = 0; i < 13; ++i) { const float v = prow[i]; a[i] = make_float2(v, v); }
 #pragma unroll
       for (int kx = 0; kx < 7; ++kx) {
-        const float4* w4 = reinterpret_cast<const float4*>(&wsm[((c * 7 + ky) * 7 + kx) * 64 + cg * 16]);
+        const float4* w4 = reinterpret_cast<const float4*>(&wsm[((c * 7 + ky) * 7 + kx) * 64]) + cg;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float4 w = w4[q];
+          const float4 w = w4[q * 4];
+          const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float av = a[2 * i + kx];
-            acc[i][4 * q + 0] = fmaf(av, w.x, acc[i][4 * q + 0]);
-            acc[i][4 * q + 1] = fmaf(av, w.y, acc[i][4 * q + 1]);
-            acc[i][4 * q + 2] = fmaf(av, w.z, acc[i][4 * q + 2]);
-            acc[i][4 * q + 3] = fmaf(av, w.w, acc[i][4 * q + 3]);
+            acc2[i][2 * q] = __ffma2_rn(a[2 * i + kx], w01, acc2[i][2 * q]);
+            acc2[i][2 * q + 1] = __ffma2_rn(a[2 * i + kx], w23, acc2[i][2 * q + 1]);
           }
         }
       }
     }
+  float acc[4][16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[i][2 * j] = acc2[i][j].x; acc[i][2 * j + 1] = acc2[i][j].y; }
   const int oy = oy0 + ty;
   if (oy >= Ho) return;
 #pragma unroll
