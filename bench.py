@@ -597,6 +597,21 @@ def run_train(args, rank, world, local_rank):
         e1.record()
         torch.cuda.synchronize()
         ar_ms = e0.elapsed_time(e1) / 10
+    # the TF32x3 tensor-core form of the forward / data-gradient convolutions (opt-in: RNC_TRAIN_CONV=tf32), same steps
+    tc_ms = None
+    if world == 1:
+        os.environ["RNC_TRAIN_CONV"] = "tf32"
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        tc_ms = e0.elapsed_time(e1) / args.steps
+        os.environ["RNC_TRAIN_CONV"] = "ffma"
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         return
@@ -621,6 +636,9 @@ def run_train(args, rank, world, local_rank):
                               "bucketed and overlapped with the backward pass"},
         "tflops_fp32": 3 * fwd_gflop * B * 1e9 / (ms / args.steps * 1e-3) / 1e12,
         "gpu_launches": int(launches), "clocks": clocks,
+        "tf32x3_convs": {"ms_per_step": tc_ms, "value": (B / (tc_ms * 1e-3)) if tc_ms else None,
+                         "note": "RNC_TRAIN_CONV=tf32: forward and data-gradient convolutions on tcgen05 kind::tf32 (hi/lo operand "
+                                 "planes, 3 MMAs per K step); per-layer error 1e-6..5e-6 instead of 1.5e-7, opt-in"},
         "gpu_eager_baseline": gpu_eager_baseline(args) if world == 1 and not args.no_cpu_baseline else None}))
 
 

@@ -127,6 +127,10 @@ typedef enum {
 #define RNC_CONV_OUT_BLOCKED 32     /* RNC_EPI_LINEAR: out_f32 in the same tile-blocked layout (produces an `add` operand)          */
 #define RNC_CONV_NO_PAIR 8          /* never use the CTA-pair (cta_group::2) form for this call */
 #define RNC_CONV_SPLIT_N 4          /* 256-column layers as two 128-column items per pixel tile (double-buffered TMEM) */
+#define RNC_CONV_TF32 64            /* operands are fp32 hi/lo planes consumed as TF32 (tcgen05 kind::tf32, K = 8): value = hi + lo with
+                                     * hi = tf32(value), 3 MMAs per K step as in the fp16 form but with fp32's exponent range — the
+                                     * training path's layers (output gradients underflow the fp16 split).  The in / w pointers address float
+                                     * planes, ld / ktot count floats, K blocks hold 32 channels, only out_f32 is written. */
 
 typedef struct {
   const float* in0; int c0; int ld0;   /* segment 0: channels [0,c0), pixel stride ld0 floats   */
@@ -185,6 +189,11 @@ int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream);
  * when |value| <= 65504). */
 int rnc_f32_to_split(const float* src, int lds, int C, long long M, void* dst_hi, void* dst_lo, int ldd, int ch_off,
                      void* stream);
+
+/* fp32 CL [M][lds] channels [0,C) -> TF32 hi/lo planes of floats [M][ldd] at channel offset ch_off: hi = value rounded to TF32
+ * (cvt.rna), lo = value - hi (operands of RNC_CONV_TF32 layers; hi + lo reproduces the value to ~2^-21). */
+int rnc_f32_to_tf32_split(const float* src, int lds, int C, long long M, float* dst_hi, float* dst_lo, int ldd, int ch_off,
+                          void* stream);
 
 /* convf1: Conv2d(2,128,7,padding=3)+ReLU on flow = coords1 - coords0 (update.py:83,92).
  * coords1 NCHW [B][2][H][W]; weight packed [49][2][Cout]; out CL. */

@@ -30,7 +30,9 @@ struct Params {
   int B, H, W;                        // output geometry
   int TW, TH, tiles_x, tiles_y, ntiles, ntn;
   int mode, kh, kw, ph, pw, stride;
-  int nblk0, nblk;                    // 64-channel blocks in segment 0 / total
+  int nblk0, nblk;                    // K blocks (128 bytes of channels: 64 halves or 32 TF32 words) in segment 0 / total
+  int bk;                             // channels per K block: 64 (fp16 hi/lo operands) or 32 (TF32 hi/lo operands)
+  int tf32;                           // operands are fp32 planes consumed as TF32 (kind::tf32): training-path layers
   int a_plane, SA, SB;                // bytes per A half-plane stage (rows*128, 1024-aligned), ring depths
   int use_base_offset;
   int resident_b;                     // the layer's whole weight matrix fits the B ring: loaded once per CTA, never released
@@ -163,7 +165,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
             ++a_it;
             mbar_wait(&a_empty[sa], pa ^ 1);
             const bool seg0 = cb < p.nblk0;
-            const int c = (seg0 ? cb : cb - p.nblk0) * kBK;
+            const int c = (seg0 ? cb : cb - p.nblk0) * p.bk;
             if (elect_one()) {
               if (PAIR) {
                 if (leader) mbar_expect_tx(&a_full[sa], 2 * a_stage);
@@ -182,7 +184,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
               ++b_it;
               if (p.resident_b && item != item0) continue;     // weights already resident
               mbar_wait(&b_empty[sb], pb ^ 1);
-              const int kcol = (tap * p.nblk + cb) * kBK;
+              const int kcol = (tap * p.nblk + cb) * p.bk;
               if (elect_one()) {
                 if (PAIR) {                  // this CTA's half of the weight rows, hi and lo planes
                   const int nrow = n0 + static_cast<int>(rank) * (BN / 2);
@@ -206,8 +208,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
     if (leader) {
-      const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>((PAIR ? 2 * kBM : kBM) >> 4) << 24);
-      const uint32_t idesc2 = (1u << 4) | (static_cast<uint32_t>((2 * BN <= 256 ? 2 * BN : BN) >> 3) << 17) | (static_cast<uint32_t>(kBM >> 4) << 24);
+      // instruction descriptor: D = F32 (bit 4), A/B format bits [7,10) / [10,13): 0 = F16, 2 = TF32; N >> 3 at 17, M >> 4 at 24
+      const uint32_t fmt = p.tf32 ? ((2u << 7) | (2u << 10)) : 0u;
+      const uint32_t idesc = (1u << 4) | fmt | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>((PAIR ? 2 * kBM : kBM) >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | fmt | (static_cast<uint32_t>((2 * BN <= 256 ? 2 * BN : BN) >> 3) << 17) | (static_cast<uint32_t>(kBM >> 4) << 24);
+      const bool tf32 = p.tf32 != 0;
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
       const int shift_rows = p.mode == MODE_ROWHALO ? 1 : p.mode == MODE_COLHALO ? p.TW : 0;
       int a_it = 0, b_it = 0, t_it = 0;
@@ -236,10 +241,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
                 if (PAIR) {
                   // M = 256 across the pair: each CTA's tensor core reads its own A rows and both CTAs' weight halves
 #pragma unroll
-                  for (int k = 0; k < kBK / 16; ++k) {
-                    umma_f16_pair(d_main, ah + 2 * k, bh + 2 * k, idesc, k == 0 ? acc : 1u);
-                    umma_f16_pair(d_corr, ah + 2 * k, bl + 2 * k, idesc, k == 0 ? acc : 1u);
-                    umma_f16_pair(d_corr, al + 2 * k, bh + 2 * k, idesc, 1);
+                  for (int k = 0; k < kBK / 16; ++k) {     // 4 K steps of 32 bytes per 128-byte block (16 halves or 8 TF32 words)
+                    if (tf32) {
+                      umma_tf32_pair(d_main, ah + 2 * k, bh + 2 * k, idesc, k == 0 ? acc : 1u);
+                      umma_tf32_pair(d_corr, ah + 2 * k, bl + 2 * k, idesc, k == 0 ? acc : 1u);
+                      umma_tf32_pair(d_corr, al + 2 * k, bh + 2 * k, idesc, 1);
+                    } else {
+                      umma_f16_pair(d_main, ah + 2 * k, bh + 2 * k, idesc, k == 0 ? acc : 1u);
+                      umma_f16_pair(d_corr, ah + 2 * k, bl + 2 * k, idesc, k == 0 ? acc : 1u);
+                      umma_f16_pair(d_corr, al + 2 * k, bh + 2 * k, idesc, 1);
+                    }
                   }
                   if (!p.resident_b) umma_commit_pair(&b_empty[sb]);
                 } else {
@@ -249,15 +260,26 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
                     // instead of twice (a 128-column instruction needs the full 128 B/clk of shared-memory bandwidth).
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
-                      umma_f16(d_main, ah + 2 * k, bh + 2 * k, idesc2, k == 0 ? acc : 1u);
-                      umma_f16(d_corr, al + 2 * k, bh + 2 * k, idesc, 1);
+                      if (tf32) {
+                        umma_tf32(d_main, ah + 2 * k, bh + 2 * k, idesc2, k == 0 ? acc : 1u);
+                        umma_tf32(d_corr, al + 2 * k, bh + 2 * k, idesc, 1);
+                      } else {
+                        umma_f16(d_main, ah + 2 * k, bh + 2 * k, idesc2, k == 0 ? acc : 1u);
+                        umma_f16(d_corr, al + 2 * k, bh + 2 * k, idesc, 1);
+                      }
                     }
                   } else {
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
-                      umma_f16(d_main, ah + 2 * k, bh + 2 * k, idesc, k == 0 ? acc : 1u);
-                      umma_f16(d_corr, ah + 2 * k, bl + 2 * k, idesc, k == 0 ? acc : 1u);
-                      umma_f16(d_corr, al + 2 * k, bh + 2 * k, idesc, 1);
+                      if (tf32) {
+                        umma_tf32(d_main, ah + 2 * k, bh + 2 * k, idesc, k == 0 ? acc : 1u);
+                        umma_tf32(d_corr, ah + 2 * k, bl + 2 * k, idesc, k == 0 ? acc : 1u);
+                        umma_tf32(d_corr, al + 2 * k, bh + 2 * k, idesc, 1);
+                      } else {
+                        umma_f16(d_main, ah + 2 * k, bh + 2 * k, idesc, k == 0 ? acc : 1u);
+                        umma_f16(d_corr, ah + 2 * k, bl + 2 * k, idesc, k == 0 ? acc : 1u);
+                        umma_f16(d_corr, al + 2 * k, bh + 2 * k, idesc, 1);
+                      }
                     }
                   }
                   if (!p.resident_b) umma_commit(&b_empty[sb]);
@@ -507,22 +529,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
 // ---------------------------------------------------------------------------------------------- host side
 // activation plane [B][Hin][Win][ld] halves: 4-D map {C, Win, Hin, B}; the box spans bw x bh input elements and is
 // traversed with element strides (sx, sy) -> (bw/sx) x (bh/sy) rows of 64 channels in shared memory
-static bool make_in_map(CUtensorMap* m, const void* base, int C, int ld, int B, int Hin, int Win, int bw, int bh, int stride) {
+static bool make_in_map(CUtensorMap* m, const void* base, int C, int ld, int B, int Hin, int Win, int bw, int bh, int stride, bool tf32) {
+  const cuuint64_t esz = tf32 ? 4 : 2;                        // 128-byte rows: 32 fp32 words or 64 halves
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B};
-  const cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)Win * ld * 2, (cuuint64_t)Hin * Win * ld * 2};
-  const cuuint32_t box[4] = {64u, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), 1};
+  const cuuint64_t strides[3] = {(cuuint64_t)ld * esz, (cuuint64_t)Win * ld * esz, (cuuint64_t)Hin * Win * ld * esz};
+  const cuuint32_t box[4] = {tf32 ? 32u : 64u, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), 1};
   const cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-  return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+  return encode_fn()(m, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // weight plane [CoutPad][Ktot] halves: 2-D map {Ktot, CoutPad}, box {64, BN}
-static bool make_w_map(CUtensorMap* m, const void* base, int ktot, int coutpad, int bn) {
+static bool make_w_map(CUtensorMap* m, const void* base, int ktot, int coutpad, int bn, bool tf32) {
   const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)coutpad};
-  const cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
-  const cuuint32_t box[2] = {64u, (cuuint32_t)bn};
+  const cuuint64_t strides[1] = {(cuuint64_t)ktot * (tf32 ? 4 : 2)};
+  const cuuint32_t box[2] = {tf32 ? 32u : 64u, (cuuint32_t)bn};
   const cuuint32_t es[2] = {1, 1};
-  return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+  return encode_fn()(m, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -620,7 +643,8 @@ extern "C" long long rnc_conv_umma_tiles(int kh, int kw, int stride, int B, int 
 // A tile is loaded more than once.
 static int choose_bn(const rnc_conv_umma_desc& d, int bn_max, int stride) {
   if (d.flags & RNC_CONV_SPLIT_N) return bn_max == 256 ? 128 : bn_max;
-  const int taps = d.kh * d.kw, ksteps = taps * ((d.c0 + 63) / 64 + (d.c1 + 63) / 64);
+  const int bkc = (d.flags & RNC_CONV_TF32) ? 32 : 64;
+  const int taps = d.kh * d.kw, ksteps = taps * ((d.c0 + bkc - 1) / bkc + (d.c1 + bkc - 1) / bkc);
   int TW, TH;
   if (stride == 1 && (d.flags & RNC_CONV_NO_HALO) == 0 && d.kw > 1 && d.W > 64) { TW = 128; TH = 1; }
   else if (stride == 1 && (d.flags & RNC_CONV_NO_HALO) == 0 && d.kw == 1 && d.kh > 1 && d.W >= 16 && d.H >= 8) { TW = 16; TH = 8; }
@@ -659,13 +683,17 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   const int Hin = d.hin > 0 ? d.hin : d.H, Win = d.win > 0 ? d.win : d.W;
   if (d.B <= 0 || d.H <= 0 || d.W <= 0 || d.cout <= 0 || d.c0 <= 0 || d.c1 < 0 || stride > 2) return RNC_ERR_BAD_SHAPE;
   if (d.kh < 1 || d.kw < 1 || !(d.kh & 1) || !(d.kw & 1) || d.kh * d.kw > 49) return RNC_ERR_BAD_SHAPE;
-  if ((d.ld0 & 7) || d.ld0 < d.c0 || (d.c1 > 0 && ((d.c0 % kBK) != 0 || (d.ld1 & 7) || d.ld1 < d.c1))) return RNC_ERR_BAD_SHAPE;
+  const bool tf32 = (d.flags & RNC_CONV_TF32) != 0;
+  const int bk = tf32 ? 32 : kBK, ldmask = tf32 ? 3 : 7;      // operand rows are 16-byte multiples
+  if (tf32 && (d.out_hi || d.epilogue == RNC_EPI_RELU_FLOW || d.epilogue == RNC_EPI_GRU_ZR || d.epilogue == RNC_EPI_TANH_RELU))
+    return RNC_ERR_UNSUPPORTED;                                // TF32 layers write fp32 outputs only
+  if ((d.ld0 & ldmask) || d.ld0 < d.c0 || (d.c1 > 0 && ((d.c0 % bk) != 0 || (d.ld1 & ldmask) || d.ld1 < d.c1))) return RNC_ERR_BAD_SHAPE;
   if (!d.in0_hi || !d.in0_lo || (d.c1 > 0 && (!d.in1_hi || !d.in1_lo)) || !d.w_hi || !d.w_lo || !d.bias) return RNC_ERR_BAD_POINTER;
   if (!aligned16(d.in0_hi) || !aligned16(d.in0_lo) || !aligned16(d.w_hi) || !aligned16(d.w_lo) || !aligned16(d.bias)) return RNC_ERR_BAD_POINTER;
   if (d.c1 > 0 && (!aligned16(d.in1_hi) || !aligned16(d.in1_lo))) return RNC_ERR_BAD_POINTER;
-  const int nblk0 = (d.c0 + kBK - 1) / kBK, nblk1 = (d.c1 + kBK - 1) / kBK, nblk = nblk0 + nblk1;
+  const int nblk0 = (d.c0 + bk - 1) / bk, nblk1 = (d.c1 + bk - 1) / bk, nblk = nblk0 + nblk1;
   const int ntaps = d.kh * d.kw;
-  if (d.ktot != ntaps * nblk * kBK) return RNC_ERR_BAD_SHAPE;          // weight planes are [coutpad][taps * blocks * 64]
+  if (d.ktot != ntaps * nblk * bk) return RNC_ERR_BAD_SHAPE;           // weight planes are [coutpad][taps * blocks * bk]
   int bn;
   if (d.coutpad <= 32) bn = 32; else if (d.coutpad <= 64) bn = 64; else if (d.coutpad <= 128) bn = 128;
   else if (d.coutpad % 192 == 0) bn = 192; else bn = 256;
@@ -732,7 +760,7 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   p.tiles_x = (d.W + TW - 1) / TW; p.tiles_y = (d.H + TH - 1) / TH;
   p.ntiles = d.B * p.tiles_x * p.tiles_y; p.ntn = d.coutpad / bn;
   p.a_plane = box_w * box_h * 128;
-  p.nblk0 = nblk0; p.nblk = nblk;
+  p.nblk0 = nblk0; p.nblk = nblk; p.bk = bk; p.tf32 = tf32 ? 1 : 0;
   p.cout = d.cout; p.epilogue = d.epilogue; p.unscale = d.unscale; p.bias = d.bias;
   p.out_f32 = d.out_f32; p.ldo_f32 = d.ldo_f32;
   p.out_hi = static_cast<__half*>(d.out_hi); p.out_lo = static_cast<__half*>(d.out_lo); p.ldo_split = d.ldo_split;
@@ -745,16 +773,17 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   if (p.aux_blocked && d.epilogue != RNC_EPI_GRU_ZR && d.epilogue != RNC_EPI_GRU_Q) return RNC_ERR_UNSUPPORTED;
 
   CUtensorMap maps[6];
-  bool ok = make_in_map(&maps[0], d.in0_hi, d.c0, d.ld0, d.B, Hin, Win, box_w, box_h, stride) &&
-            make_in_map(&maps[1], d.in0_lo, d.c0, d.ld0, d.B, Hin, Win, box_w, box_h, stride);
+  bool ok = make_in_map(&maps[0], d.in0_hi, d.c0, d.ld0, d.B, Hin, Win, box_w, box_h, stride, tf32) &&
+            make_in_map(&maps[1], d.in0_lo, d.c0, d.ld0, d.B, Hin, Win, box_w, box_h, stride, tf32);
   if (d.c1 > 0) {
-    ok = ok && make_in_map(&maps[2], d.in1_hi, d.c1, d.ld1, d.B, Hin, Win, box_w, box_h, stride) &&
-         make_in_map(&maps[3], d.in1_lo, d.c1, d.ld1, d.B, Hin, Win, box_w, box_h, stride);
+    ok = ok && make_in_map(&maps[2], d.in1_hi, d.c1, d.ld1, d.B, Hin, Win, box_w, box_h, stride, tf32) &&
+         make_in_map(&maps[3], d.in1_lo, d.c1, d.ld1, d.B, Hin, Win, box_w, box_h, stride, tf32);
   } else {
     maps[2] = maps[0]; maps[3] = maps[1];
   }
   const bool pair = umma::pair_enabled() && (d.flags & RNC_CONV_NO_PAIR) == 0;
-  ok = ok && make_w_map(&maps[4], d.w_hi, d.ktot, d.coutpad, pair ? bn / 2 : bn) && make_w_map(&maps[5], d.w_lo, d.ktot, d.coutpad, pair ? bn / 2 : bn);
+  ok = ok && make_w_map(&maps[4], d.w_hi, d.ktot, d.coutpad, pair ? bn / 2 : bn, tf32) &&
+       make_w_map(&maps[5], d.w_lo, d.ktot, d.coutpad, pair ? bn / 2 : bn, tf32);
   if (!ok) return RNC_ERR_BAD_SHAPE;
 
   cudaStream_t s = as_stream(stream);

@@ -192,6 +192,22 @@ __global__ void f32_to_split_kernel(const float* __restrict__ src, int lds, int 
   }
 }
 
+// ---------------------------------------------------------------- fp32 CL -> TF32 hi/lo planes (training-path tensor-core layers)
+__global__ void f32_to_tf32_split_kernel(const float* __restrict__ src, int lds, int C, long long M, float* __restrict__ hi,
+                                         float* __restrict__ lo, int ldd, int ch_off) {
+  const long long n = M * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / C;
+    const int c = (int)(i - m * C);
+    const float v = src[m * lds + c];
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+    const float h = __uint_as_float(t);
+    hi[m * ldd + ch_off + c] = h;
+    lo[m * ldd + ch_off + c] = v - h;
+  }
+}
+
 // ---------------------------------------------------------------- convex upsampling (raft.py:73-84)
 __global__ void __launch_bounds__(256)
 convex_upsample_kernel(const float* __restrict__ flow, const float* __restrict__ mask, int ldm, int B, int H8, int W8,
@@ -376,6 +392,16 @@ int rnc_f32_to_split(const float* src, int lds, int C, long long M, void* dst_hi
   if (blocks > 148 * 32) blocks = 148 * 32;
   f32_to_split_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(src, lds, C, M, static_cast<__half*>(dst_hi),
                                                                  static_cast<__half*>(dst_lo), ldd, ch_off);
+  return after_launch();
+}
+
+int rnc_f32_to_tf32_split(const float* src, int lds, int C, long long M, float* dst_hi, float* dst_lo, int ldd, int ch_off,
+                          void* stream) {
+  if (C <= 0 || M <= 0 || lds < C || ldd < C + ch_off || ch_off < 0) return RNC_ERR_BAD_SHAPE;
+  if (!src || !dst_hi || !dst_lo) return RNC_ERR_BAD_POINTER;
+  long long blocks = (M * C + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  f32_to_tf32_split_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(src, lds, C, M, dst_hi, dst_lo, ldd, ch_off);
   return after_launch();
 }
 

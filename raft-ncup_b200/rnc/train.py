@@ -47,58 +47,91 @@ def _ceil4(c):
     return (c + 3) // 4 * 4
 
 
-def _umma_ok(eng, Cx, cout):
-    """The tensor-core convolution (fp16 hi/lo split operands, fp32-faithful: 3 MMAs per K step) serves a training-path layer when
-    its operand pitch is a multiple of 8 halves and its fp32 output row needs no wider padding than the channel-last tensors use
-    (the kernel stores whole 32-channel chunks).  Thin layers (flow, image, 2-channel heads) stay on the exact CUDA-core kernel."""
+def _conv_mode():
+    """RNC_TRAIN_CONV selects how the training path's convolutions (forward and data gradient) run:
+      ffma (default)  exact fp32 on CUDA cores (rnc_conv2d_cl_fwd): per-layer error 1.5e-7; every non-fnet parameter's gradient
+                      within 1e-3 of the reference's autograd (cfg 5 step on B200: 149 ms)
+      tf32            tcgen05 kind::tf32 on TF32 hi/lo operand planes, 3 MMAs per K step (x_hi*w_hi + x_hi*w_lo + x_lo*w_hi):
+                      ~2^-21 per product (per-layer 1e-6 .. 5e-6) with fp32's exponent range, so output gradients of 1e-9
+                      survive; 112 ms per step, ill-conditioned parameters (cnet.conv1) move to 5e-3
+      umma            fp16 hi/lo split operands (the inference kernels): output gradients underflow the split's normal range —
+                      per-parameter gradient errors of 5e-3 (forward only) to 4e-2 (with RNC_TRAIN_DGRAD=umma)
+    Parity first: the default is the exact path; the tensor-core forms are opt-in and reported beside it by bench.py."""
     import os
-    # Opt-in (RNC_TRAIN_CONV=umma): measured on B200 at cfg 5 the step drops from 149 to 127 ms with the forward convolutions on
-    # tensor cores (110 ms with the data gradients too), but the per-parameter gradient agreement with the reference's autograd
-    # degrades from <= 1e-3 to 5e-3 (4e-2 with split-operand data gradients: output gradients underflow the fp16 split's normal
-    # range).  Parity first: the default training path is exact fp32 end to end.
-    if eng.mode != "umma" or os.environ.get("RNC_TRAIN_CONV", "ffma") != "umma":
-        return False
-    return Cx % 8 == 0 and Cx >= 32 and cout >= 32 and (cout + 31) // 32 * 32 == _ceil4(cout)
+    return os.environ.get("RNC_TRAIN_CONV", "ffma")
 
 
-def _dgrad_umma():
+def _umma_ok(eng, Cx, cout, dgrad=False):
+    """Can this layer run on the tensor-core convolution?  The kernel stores whole 32-channel chunks of fp32 output, so the
+    output row must not need wider padding than the channel-last tensors use; the fp16 form also needs a pitch of 8 halves."""
     import os
-    return os.environ.get("RNC_TRAIN_DGRAD", "ffma") == "umma"
+    mode = _conv_mode()
+    if eng.mode != "umma" or mode == "ffma" or (cout + 31) // 32 * 32 != _ceil4(cout):
+        return None
+    if mode == "tf32":
+        return "tf32" if Cx % 4 == 0 else None
+    if dgrad and os.environ.get("RNC_TRAIN_DGRAD", "ffma") != "umma":
+        return None
+    return "f16" if Cx % 8 == 0 and Cx >= 32 and cout >= 32 else None
 
 
-def _packed_umma(weight, kind, cin_pad):
+class _WeightsTF32:
+    """[Cout,Cin,KH,KW] -> TF32 hi/lo planes of floats [CoutPad][taps * blocks * 32] (hi = round-to-nearest TF32, lo = w - hi), the
+    operand format of RNC_CONV_TF32 layers; no scaling is needed (fp32 exponent range)."""
+
+    def __init__(self, w, cin_pad):
+        from .engine_umma import _coutpad
+        cout, cin, kh, kw = w.shape
+        nblk = (cin_pad + 31) // 32
+        self.cout, self.kh, self.kw = cout, kh, kw
+        self.coutpad = _coutpad(cout)
+        self.ktot = kh * kw * nblk * 32
+        wp = torch.zeros(self.coutpad, kh * kw, nblk * 32, dtype=torch.float32, device=w.device)
+        wp[:cout, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
+        ws = wp.reshape(self.coutpad, self.ktot)
+        self.w_hi = ((ws.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32).contiguous()
+        self.w_lo = (ws - self.w_hi).contiguous()
+        self.unscale = 1.0
+        self.bias = torch.zeros(self.coutpad, dtype=torch.float32, device=w.device)
+
+
+def _packed_umma(weight, kind, cin_pad, fmt="f16"):
     from .engine_umma import UmmaWeights
-    key = (id(weight), weight._version, kind + "_umma", cin_pad)
+    key = (id(weight), weight._version, kind + "_" + fmt, cin_pad)
     hit = _PACK_CACHE.get(key)
     if hit is None or hit[0] is not weight:
         w = weight.detach().float()
         if kind == "dgrad":
             w = w.flip(2, 3).transpose(0, 1)
-        if w.shape[1] != cin_pad:
-            w = F.pad(w, (0, 0, 0, 0, 0, cin_pad - w.shape[1]))
-        # fixed scale 2^10 (no device sync per pack): exact for |w| < 32; a lo part below the half normal range only costs an
-        # absolute 2^-34 per weight
-        hit = _PACK_CACHE[key] = (weight, UmmaWeights(w.contiguous(), None, [cin_pad], scale_log2=10))
+        if fmt == "tf32":
+            packed = _WeightsTF32(w.contiguous(), cin_pad)
+        else:
+            if w.shape[1] != cin_pad:
+                w = F.pad(w, (0, 0, 0, 0, 0, cin_pad - w.shape[1]))
+            # fixed scale 2^10 (no device sync per pack): exact for |w| < 32; a lo part below the half normal range only costs an
+            # absolute 2^-34 per weight
+            packed = UmmaWeights(w.contiguous(), None, [cin_pad], scale_log2=10)
+        hit = _PACK_CACHE[key] = (weight, packed)
     return hit[1]
 
 
-def _conv_launch_umma(eng, x, wt, cout, stride=1, bias=None):
-    """Same contract as _conv_launch on the tcgen05 path: x fp32 CL -> split halves (rnc_f32_to_split) -> rnc_conv2d_umma_fwd with
-    an fp32 channel-last output; stride 2 is native (TMA element strides), no subsampling pass."""
-    from .engine_umma import SplitBuf
+def _conv_launch_umma(eng, x, wt, cout, stride=1, bias=None, fmt="f16"):
+    """Same contract as _conv_launch on the tcgen05 path: x fp32 CL -> hi/lo operand planes (halves or TF32 words) ->
+    rnc_conv2d_umma_fwd with an fp32 channel-last output; stride 2 is native (TMA element strides), no subsampling pass."""
     B, H, W, Cx = x.shape
     Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
     M = B * H * W
-    xs = SplitBuf.__new__(SplitBuf)
-    xs.hi = torch.empty(M, Cx, dtype=torch.float16, device=x.device)
-    xs.lo = torch.empty(M, Cx, dtype=torch.float16, device=x.device)
-    xs.ld = Cx
-    native.check(eng.L.rnc_f32_to_split(_ptr(x), Cx, Cx, M, _ptr(xs.hi), _ptr(xs.lo), Cx, 0, _stream()), "f32_to_split")
+    dt = torch.float32 if fmt == "tf32" else torch.float16
+    hi = torch.empty(M, Cx, dtype=dt, device=x.device)
+    lo = torch.empty(M, Cx, dtype=dt, device=x.device)
+    split = eng.L.rnc_f32_to_tf32_split if fmt == "tf32" else eng.L.rnc_f32_to_split
+    native.check(split(_ptr(x), Cx, Cx, M, _ptr(hi), _ptr(lo), Cx, 0, _stream()), "operand split")
     ldo = _ceil4(cout)
     out = torch.empty(B, Ho, Wo, ldo, dtype=torch.float32, device=x.device)
     if bias is not None:
-        wt = _with_bias(wt, bias)
-    eng.uconv(B, Ho, Wo, xs.ptrs(), Cx, Cx, wt, native.EPI_LINEAR, out_f32=out.data_ptr(), ldo_f32=ldo, stride=stride, hin=H, win=W)
+        wt = _WithBias(wt, bias)
+    eng.uconv(B, Ho, Wo, (hi.data_ptr(), lo.data_ptr()), Cx, Cx, wt, native.EPI_LINEAR, out_f32=out.data_ptr(), ldo_f32=ldo,
+              stride=stride, hin=H, win=W, flags=eng.conv_flags | (native.CONV_TF32 if fmt == "tf32" else 0))
     return out
 
 
@@ -110,10 +143,6 @@ class _WithBias:
         b = torch.zeros_like(wt.bias)
         b[:wt.cout] = bias.detach()
         self.bias = b
-
-
-def _with_bias(wt, bias):
-    return _WithBias(wt, bias)
 
 
 def _conv_launch(eng, x, packed, cout, kh, kw, bias=None):
@@ -151,8 +180,9 @@ class ConvCL(torch.autograd.Function):
             raise ValueError("ConvCL: input must be channel-last with ceil4(Cin) channels")
         if stride not in (1, 2):
             raise NotImplementedError("stride 1 or 2")
-        if _umma_ok(eng, Cx, cout):
-            y = _conv_launch_umma(eng, x, _packed_umma(weight, "fwd", Cx), cout, stride, bias)
+        fmt = _umma_ok(eng, Cx, cout)
+        if fmt:
+            y = _conv_launch_umma(eng, x, _packed_umma(weight, "fwd", Cx, fmt), cout, stride, bias, fmt)
         else:
             y = _conv_launch(eng, x, _packed(weight, "fwd", Cx), cout, kh, kw, bias)
             if stride == 2:
@@ -176,11 +206,9 @@ class ConvCL(torch.autograd.Function):
                 if ctx.stride == 2:
                     g_full = torch.zeros(B, H, W, ldg, dtype=torch.float32, device=x.device)
                     g_full[:, ::2, ::2] = gy
-                # The data gradient stays on the exact fp32 kernel by default: output gradients span 1e-9 .. 1e-2 here, below the
-                # normal range of the fp16 hi/lo split (measured: per-parameter gradient errors of 1-4e-2 with split operands
-                # against 1e-4 with fp32) — a per-tensor power-of-two gradient scale would be needed (RNC_TRAIN_DGRAD=umma).
-                if _umma_ok(eng, ldg, cin) and _dgrad_umma():
-                    gx = _conv_launch_umma(eng, g_full, _packed_umma(weight, "dgrad", ldg), cin)
+                fmt = _umma_ok(eng, ldg, cin, dgrad=True)
+                if fmt:
+                    gx = _conv_launch_umma(eng, g_full, _packed_umma(weight, "dgrad", ldg, fmt), cin, fmt=fmt)
                 else:
                     gx = _conv_launch(eng, g_full, _packed(weight, "dgrad", ldg), cin, kh, kw)
                 if gx.shape[-1] != Cx:               # Cx > ceil4(cin) never happens; equal by construction
