@@ -128,9 +128,11 @@ conv_wgrad_kernel(const float* __restrict__ x, int ldx, int cin, const float* __
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
   float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const bool do_bias = gb != nullptr && tap == 0 && ci0 == 0 && ty == 0;
-  // staging: 16 px x 64 ch = 256 float4 per operand, 4 per thread: pixel = (tid >> 4) + 4 * i, channel quad = tid & 15
+  // staging: 16 px x 64 ch = 256 float4 per operand, 4 per thread: pixel = (tid >> 4) + 4 * i, channel quad = tid & 15.
+  // Register double buffering: the global loads of step k+1 are issued before the FMAs of step k.
   const int sq = tid & 15;
-  for (long long pb = p0; pb < p1; pb += WK) {
+  float4 xr[4], gr[4];
+  auto fetch = [&](long long pb) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int sp = (tid >> 4) + 4 * i;
@@ -141,17 +143,26 @@ conv_wgrad_kernel(const float* __restrict__ x, int ldx, int cin, const float* __
         const int yo = r / Wo, xo = r - yo * Wo;
         const int yi = yo * stride + ky - ph, xi = xo * stride + kx - pw;
         if (yi >= 0 && yi < Hin && xi >= 0 && xi < Win && ci0 + 4 * sq < cin)
-          xv = *reinterpret_cast<const float4*>(x + ((static_cast<size_t>(b) * Hin + yi) * Win + xi) * ldx + ci0 + 4 * sq);
+          xv = __ldg(reinterpret_cast<const float4*>(x + ((static_cast<size_t>(b) * Hin + yi) * Win + xi) * ldx + ci0 + 4 * sq));
         if (co0 + 4 * sq < cout) {
           const float* gp = gy + static_cast<size_t>(p) * ldg + co0 + 4 * sq;
-          if (co0 + 4 * sq + 4 <= cout) gv = *reinterpret_cast<const float4*>(gp);
+          if (co0 + 4 * sq + 4 <= cout) gv = __ldg(reinterpret_cast<const float4*>(gp));
           else { gv.x = gp[0]; if (co0 + 4 * sq + 1 < cout) gv.y = gp[1]; if (co0 + 4 * sq + 2 < cout) gv.z = gp[2]; }
         }
       }
-      *reinterpret_cast<float4*>(&Xs[sp][4 * sq]) = xv;
-      *reinterpret_cast<float4*>(&Gs[sp][4 * sq]) = gv;
+      xr[i] = xv; gr[i] = gv;
+    }
+  };
+  fetch(p0);
+  for (long long pb = p0; pb < p1; pb += WK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int sp = (tid >> 4) + 4 * i;
+      *reinterpret_cast<float4*>(&Xs[sp][4 * sq]) = xr[i];
+      *reinterpret_cast<float4*>(&Gs[sp][4 * sq]) = gr[i];
     }
     __syncthreads();
+    if (pb + WK < p1) fetch(pb + WK);
 #pragma unroll
     for (int k = 0; k < WK; ++k) {
       const float4 x0 = *reinterpret_cast<const float4*>(&Xs[k][ty * 8]), x1 = *reinterpret_cast<const float4*>(&Xs[k][ty * 8 + 4]);
