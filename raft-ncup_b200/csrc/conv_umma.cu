@@ -24,6 +24,9 @@ constexpr int kThreads = 320;        // warp 0: TMA producer, warp 1: MMA issuer
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kMaxSA = 4, kMaxSB = 12;
+constexpr int kStageWarp = 4096;     // epilogue staging per epilogue warp: 32 px x 32 ch as [hi 2 KB | lo 2 KB] halves or 4 KB of fp32
+constexpr int kStageBytes = 8 * kStageWarp;
+constexpr int kRingBudget = 184 * 1024;   // A + B rings; + barriers, statistics slots and the epilogue staging = 227 KB
 enum { MODE_TAP = 0, MODE_ROWHALO = 1, MODE_COLHALO = 2 };
 
 struct Params {
@@ -95,7 +98,9 @@ template <int BN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__ CUtensorMap mA0l,
                  const __grid_constant__ CUtensorMap mA1h, const __grid_constant__ CUtensorMap mA1l,
-                 const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, const Params p) {
+                 const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl,
+                 const __grid_constant__ CUtensorMap mOh, const __grid_constant__ CUtensorMap mOl,
+                 const __grid_constant__ CUtensorMap mHf, const Params p) {
   using C = Cfg<BN>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -112,6 +117,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   double* stat_acc = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(bars) + 512);   // [8 warps][kHalfN][32 lanes][2], BN <= 128 only
+  // epilogue staging (TMA-store source), 1024-aligned so the 64B / 128B swizzle patterns are functions of the buffer offset
+  unsigned char* stage_base = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(bars) + 512 + (BN <= 128 ? 8192 : 0) + 1023) & ~uintptr_t(1023));
 
   pdl_trigger();                       // the next kernel in the stream may begin its prologue on SMs this grid has left
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -321,6 +329,43 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
       for (int ci = 0; ci < kHalfN; ++ci) { my_acc[ci * 64] = 0.0; my_acc[ci * 64 + 1] = 0.0; }
     }
     const uint32_t acc_empty_l = PAIR ? mapa_u32(smem_u32(acc_empty), 0) : 0u;     // the leader's MMA warp waits for both CTAs
+    // Outputs leave through shared memory and TMA stores: a warp's 32 px x 32 ch chunk is one box of the output tensor
+    // (full 64- / 128-byte rows per pixel instead of 16-byte pieces per thread; image borders and ghost tiles are clipped by
+    // the TMA unit).  The staging rows are written with the map's swizzle (64B for halves, 128B for fp32): conflict-free.
+    unsigned char* stg = stage_base + (warp - 2) * kStageWarp;
+    bool stg_busy = false;                         // warp-uniform: a TMA store may still be reading the staging buffer
+    const int lgx = (lg * 32) % p.TW, lgy = (lg * 32) / p.TW;
+    int bx = 0, by = 0, bb = 0;                    // box origin of this warp's lane group in the current tile
+    auto stage_free = [&]() {
+      if (stg_busy) { if (lane == 0) bulk_wait_read0(); __syncwarp(); stg_busy = false; }
+    };
+    auto store_split = [&](const float* v, int ch) {           // hi/lo halves of v[0..32) -> channels [ch, ch+32) of out_hi / out_lo
+      stage_free();
+      uint4* sh = reinterpret_cast<uint4*>(stg + lane * 64);
+      uint4* sl = reinterpret_cast<uint4*>(stg + 2048 + lane * 64);
+      const int sw = (lane >> 1) & 3;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) split8(v + 8 * q, sh[q ^ sw], sl[q ^ sw]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(&mOh, stg, ch, bx, by, bb);
+        tma_store_4d(&mOl, stg + 2048, ch, bx, by, bb);
+        bulk_commit();
+      }
+      stg_busy = true;
+    };
+    auto store_h = [&](const float* v, int ch) {               // fp32 v[0..32) -> channels [ch, ch+32) of h
+      stage_free();
+      float4* sf = reinterpret_cast<float4*>(stg + lane * 128);
+      const int sw = lane & 7;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) sf[q ^ sw] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { tma_store_4d(&mHf, stg, ch, bx, by, bb); bulk_commit(); }
+      stg_busy = true;
+    };
     int t_it = 0;
     for (int item = item0; item < items; item += item_step, ++t_it) {
       const int ptile = item / p.ntn, n0 = (item - ptile * p.ntn) * BN;
@@ -328,8 +373,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
       const int b = tile / tpi, tr = tile - b * tpi;
       const bool ghost = tile >= p.ntiles;                     // odd tile count: the pair's second CTA idles through this item
       if (use_stats && !ghost && (b != acc_b || n0 != acc_n0)) { flush_stats(); acc_b = b; acc_n0 = n0; }
-      const int y = (tr / p.tiles_x) * p.TH + ml / p.TW, x = (tr % p.tiles_x) * p.TW + ml % p.TW;
+      const int ty0 = (tr / p.tiles_x) * p.TH, tx0 = (tr % p.tiles_x) * p.TW;
+      const int y = ty0 + ml / p.TW, x = tx0 + ml % p.TW;
       const bool valid = !ghost && y < p.H && x < p.W;
+      bx = tx0 + lgx; by = ty0 + lgy; bb = b;                  // a ghost tile has b >= B: its boxes are clipped whole
       // tile-blocked tensors (p.aux_blocked / p.out_blocked): element (tile, channel c, row ml) at ((tile * ld + c) * 128 + ml),
       // so a warp's 32 pixels are contiguous per channel
       const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
@@ -345,7 +392,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + buf * 2 * BN + cc * 32;
         tmem_ld32(taddr, r);
         tmem_ld32(taddr + BN, rc);
-        if (!valid && !use_stats) continue;
+        if (ghost) continue;                                           // warp-uniform: nothing to add to the statistics either
         float v[32];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -381,65 +428,71 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
           warp_transpose_sum(s2, lane);
           my_acc[(cc - cc0) * 64] += static_cast<double>(s1[0]);
           my_acc[(cc - cc0) * 64 + 1] += static_cast<double>(s2[0]);
-          if (!valid) continue;
         }
         if (epi == RNC_EPI_GRU_ZR) {
           const int Ch = p.cout >> 1;
           if (n < Ch) {            // z gate -> fp32 aux buffer
-            if (p.aux_blocked) {
-              float* dst = p.aux0 + (static_cast<size_t>(tile) * p.ldaux + n) * kBM + ml;
+            if (valid) {
+              if (p.aux_blocked) {
+                float* dst = p.aux0 + (static_cast<size_t>(tile) * p.ldaux + n) * kBM + ml;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(j) * kBM] = sigmoid_fast(v[j]);
-            } else {
-              float4* dst = reinterpret_cast<float4*>(p.aux0 + pix * p.ldaux + n);
+                for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(j) * kBM] = sigmoid_fast(v[j]);
+              } else {
+                float4* dst = reinterpret_cast<float4*>(p.aux0 + pix * p.ldaux + n);
 #pragma unroll
-              for (int q = 0; q < 8; ++q)
-                dst[q] = make_float4(sigmoid_fast(v[4 * q]), sigmoid_fast(v[4 * q + 1]), sigmoid_fast(v[4 * q + 2]), sigmoid_fast(v[4 * q + 3]));
+                for (int q = 0; q < 8; ++q)
+                  dst[q] = make_float4(sigmoid_fast(v[4 * q]), sigmoid_fast(v[4 * q + 1]), sigmoid_fast(v[4 * q + 2]), sigmoid_fast(v[4 * q + 3]));
+              }
             }
           } else {                 // r gate -> r*h as split halves
             const float4* hp = reinterpret_cast<const float4*>(p.h + pix * p.ldh + (n - Ch));
-            float4 hreg[8];        // all loads first (h is read-only here): no load->store serialisation
+            float4 hreg[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) hreg[q] = __ldg(hp + q);
+            for (int q = 0; q < 8; ++q) hreg[q] = valid ? __ldg(hp + q) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const float4 hv = hreg[q];
               v[4 * q + 0] = sigmoid_fast(v[4 * q + 0]) * hv.x; v[4 * q + 1] = sigmoid_fast(v[4 * q + 1]) * hv.y;
               v[4 * q + 2] = sigmoid_fast(v[4 * q + 2]) * hv.z; v[4 * q + 3] = sigmoid_fast(v[4 * q + 3]) * hv.w;
             }
-            uint4* dh = reinterpret_cast<uint4*>(p.out_hi + pix * p.ldo_split + (n - Ch));
-            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + pix * p.ldo_split + (n - Ch));
-#pragma unroll
-            for (int q = 0; q < 4; ++q) split8(v + 8 * q, dh[q], dl[q]);
+            store_split(v, n - Ch);
           }
           continue;
         }
         if (epi == RNC_EPI_FLOW_DELTA) {
           // FlowHead.conv2 + `coords1 = coords1 + delta_flow` (update.py:14, raft_nc_dbl.py:157); only channels 0,1 are real
-          const int HW = p.H * p.W;
-          const size_t i0 = static_cast<size_t>(b) * 2 * HW + y * p.W + x;
-          p.aux0[i0] += v[0];
-          p.aux0[i0 + HW] += v[1];
-          if (p.out_f32) { p.out_f32[i0] = v[0]; p.out_f32[i0 + HW] = v[1]; }
+          if (valid) {
+            const int HW = p.H * p.W;
+            const size_t i0 = static_cast<size_t>(b) * 2 * HW + y * p.W + x;
+            p.aux0[i0] += v[0];
+            p.aux0[i0 + HW] += v[1];
+            if (p.out_f32) { p.out_f32[i0] = v[0]; p.out_f32[i0 + HW] = v[1]; }
+          }
           continue;
         }
         bool want_f32 = p.out_f32 != nullptr;
         if (epi == RNC_EPI_GRU_Q) {
-          float4* hp = reinterpret_cast<float4*>(p.h + pix * p.ldh + n);
-          float4 zreg[8], hreg[8];   // issue every load before the first store (hp is read-modify-write)
-          if (p.aux_blocked) {
-            const float* zb = p.aux0 + (static_cast<size_t>(tile) * p.ldaux + n) * kBM + ml;
+          const float4* hp = reinterpret_cast<const float4*>(p.h + pix * p.ldh + n);
+          float4 zreg[8], hreg[8];
+          if (!valid) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-              zreg[q] = make_float4(__ldg(zb + static_cast<size_t>(4 * q) * kBM), __ldg(zb + static_cast<size_t>(4 * q + 1) * kBM),
-                                    __ldg(zb + static_cast<size_t>(4 * q + 2) * kBM), __ldg(zb + static_cast<size_t>(4 * q + 3) * kBM));
+            for (int q = 0; q < 8; ++q) { zreg[q] = make_float4(0.f, 0.f, 0.f, 0.f); hreg[q] = zreg[q]; }
           } else {
-            const float4* zp = reinterpret_cast<const float4*>(p.aux0 + pix * p.ldaux + n);
+            if (p.aux_blocked) {
+              const float* zb = p.aux0 + (static_cast<size_t>(tile) * p.ldaux + n) * kBM + ml;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) zreg[q] = __ldg(zp + q);
+              for (int q = 0; q < 8; ++q)
+                zreg[q] = make_float4(__ldg(zb + static_cast<size_t>(4 * q) * kBM), __ldg(zb + static_cast<size_t>(4 * q + 1) * kBM),
+                                      __ldg(zb + static_cast<size_t>(4 * q + 2) * kBM), __ldg(zb + static_cast<size_t>(4 * q + 3) * kBM));
+            } else {
+              const float4* zp = reinterpret_cast<const float4*>(p.aux0 + pix * p.ldaux + n);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) zreg[q] = __ldg(zp + q);
+            }
+            // plain loads: h is rewritten by this kernel (each chunk is read before its own TMA store is issued)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) hreg[q] = hp[q];
           }
-#pragma unroll
-          for (int q = 0; q < 8; ++q) hreg[q] = hp[q];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 z = zreg[q], hv = hreg[q];
@@ -447,12 +500,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
             v[4 * q + 1] = (1.f - z.y) * hv.y + z.y * tanh_fast(v[4 * q + 1]);
             v[4 * q + 2] = (1.f - z.z) * hv.z + z.z * tanh_fast(v[4 * q + 2]);
             v[4 * q + 3] = (1.f - z.w) * hv.w + z.w * tanh_fast(v[4 * q + 3]);
-            hp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
+          store_h(v, n);
         } else if (epi == RNC_EPI_RELU || epi == RNC_EPI_RELU_FLOW) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          if (epi == RNC_EPI_RELU_FLOW && n <= p.cout && p.cout < n + 32) {
+          if (epi == RNC_EPI_RELU_FLOW && n <= p.cout && p.cout < n + 32 && valid) {
             // append flow = coords1 - grid as channels [cout, cout+2)  (update.py:97)
             const int HW = p.H * p.W;
             const float* c1 = p.aux0 + static_cast<size_t>(b) * 2 * HW + y * p.W + x;
@@ -471,7 +524,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
           const float4* rp = reinterpret_cast<const float4*>(p.res + pix * p.ldres + n);
           float4 rreg[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) rreg[q] = __ldg(rp + q);
+          for (int q = 0; q < 8; ++q) rreg[q] = valid ? __ldg(rp + q) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             v[4 * q + 0] = fmaxf(rreg[q].x + fmaxf(v[4 * q + 0], 0.f), 0.f);
@@ -490,7 +543,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
             want_f32 = false;
           }
         }
-        if (want_f32) {
+        if (want_f32 && valid) {
           if (p.out_blocked) {
             float* dst = p.out_f32 + (static_cast<size_t>(tile) * p.ldo_f32 + n) * kBM + ml;
 #pragma unroll
@@ -501,12 +554,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
             for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
         }
-        if (p.out_hi) {
-          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + pix * p.ldo_split + n);
-          uint4* dl = reinterpret_cast<uint4*>(p.out_lo + pix * p.ldo_split + n);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) split8(v + 8 * q, dh[q], dl[q]);
-        }
+        if (p.out_hi) store_split(v, n);
       }
       // this warp has finished reading the accumulator buffer (tcgen05.wait::ld inside tmem_ld32)
       tcgen05_fence_before();
@@ -514,6 +562,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
       if (lane == 0) { if (PAIR) mbar_arrive_cluster(acc_empty_l + buf * 8); else mbar_arrive(&acc_empty[buf]); }
     }
     if (use_stats) flush_stats();
+    if (lane == 0) bulk_wait_all0();               // the staging buffer must outlive its TMA stores; their writes complete here
   }
 
   // ------------------------------------------------------------------ teardown
@@ -550,6 +599,19 @@ static bool make_w_map(CUtensorMap* m, const void* base, int ktot, int coutpad, 
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// output plane [B][H][W][ld] (halves or fp32): 4-D map {C, W, H, B}, box = 32 channels x one lane group's bw x bh pixels,
+// rows swizzled (64B for halves, 128B for fp32) to match the epilogue's conflict-free staging writes
+static bool make_out_map(CUtensorMap* m, const void* base, int C, int ld, int B, int H, int W, int bw, int bh, bool f32) {
+  const cuuint64_t esz = f32 ? 4 : 2;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)ld * esz, (cuuint64_t)W * ld * esz, (cuuint64_t)H * W * ld * esz};
+  const cuuint32_t box[4] = {32u, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  return encode_fn()(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int sm_count() {
   static int n = 0;
   if (!n) {
@@ -564,8 +626,8 @@ template <int BN, bool PAIR>
 static int launch(const CUtensorMap* maps, Params& p, cudaStream_t stream, int max_sa, int max_sb) {
   using C = Cfg<BN>;
   const int a_stage = 2 * p.a_plane;
-  // ring depths within ~208 KB: both rings hide the same TMA latency, so deepen A (up to 4) while B keeps >= 3 stages
-  const int budget = 208 * 1024, b_stage = PAIR ? C::kBTile : 2 * C::kBTile;      // a pair's CTA stages half of the weight rows
+  // ring depths within kRingBudget: both rings hide the same TMA latency, so deepen A (up to 4) while B keeps >= 3 stages
+  const int budget = kRingBudget, b_stage = PAIR ? C::kBTile : 2 * C::kBTile;      // a pair's CTA stages half of the weight rows
   p.SA = 2;
   while (p.SA < kMaxSA && budget - (p.SA + 1) * a_stage >= 3 * b_stage) ++p.SA;
   int sb = (budget - p.SA * a_stage) / b_stage;
@@ -577,13 +639,14 @@ static int launch(const CUtensorMap* maps, Params& p, cudaStream_t stream, int m
   p.resident_b = 0;
   {
     const int nb = p.kh * p.kw * p.nblk;
-    const int hard = 227 * 1024 - 1024 - 512 - 8192 - 1024;
+    const int hard = 227 * 1024 - 1024 - 512 - 8192 - 1024 - kStageBytes;
     if (p.ntn == 1 && nb <= kMaxSB && nb > p.SB && max_sb == 0 && 2 * a_stage + nb * b_stage <= hard) {
       p.resident_b = 1; p.SB = nb; p.SA = (hard - nb * b_stage) / a_stage;
       if (p.SA > kMaxSA) p.SA = kMaxSA;
     }
   }
-  const int smem = p.SA * a_stage + p.SB * b_stage + 1024 + 512 + (BN <= 128 ? 8192 : 0);   // + fp64 statistics slots
+  // + alignment slack, barriers, fp64 statistics slots, 1024-aligned epilogue staging
+  const int smem = p.SA * a_stage + p.SB * b_stage + 1024 + 512 + (BN <= 128 ? 8192 : 0) + 1024 + kStageBytes;
   static unsigned long long done = 0;
   if (int st = ensure_dyn_smem(conv_umma_kernel<BN, PAIR>, 227 * 1024, &done)) return st;
   const int items = (PAIR ? (p.ntiles + 1) / 2 : p.ntiles) * p.ntn;
@@ -604,7 +667,8 @@ static int launch(const CUtensorMap* maps, Params& p, cudaStream_t stream, int m
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, PAIR>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, PAIR>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7],
+                                     maps[8], p);
   if (e != cudaSuccess) { g_last_cuda_error = static_cast<int>(e); return RNC_ERR_CUDA; }
   return after_launch();
 }
@@ -772,7 +836,7 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   if (p.out_blocked && (d.epilogue != RNC_EPI_LINEAR || d.out_hi || d.stats)) return RNC_ERR_UNSUPPORTED;
   if (p.aux_blocked && d.epilogue != RNC_EPI_GRU_ZR && d.epilogue != RNC_EPI_GRU_Q) return RNC_ERR_UNSUPPORTED;
 
-  CUtensorMap maps[6];
+  CUtensorMap maps[9];
   bool ok = make_in_map(&maps[0], d.in0_hi, d.c0, d.ld0, d.B, Hin, Win, box_w, box_h, stride, tf32) &&
             make_in_map(&maps[1], d.in0_lo, d.c0, d.ld0, d.B, Hin, Win, box_w, box_h, stride, tf32);
   if (d.c1 > 0) {
@@ -784,6 +848,25 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   const bool pair = umma::pair_enabled() && (d.flags & RNC_CONV_NO_PAIR) == 0;
   ok = ok && make_w_map(&maps[4], d.w_hi, d.ktot, d.coutpad, pair ? bn / 2 : bn, tf32) &&
        make_w_map(&maps[5], d.w_lo, d.ktot, d.coutpad, pair ? bn / 2 : bn, tf32);
+  // epilogue stores: out_hi / out_lo (and h for the q gate) as boxes of 32 channels x one TMEM lane group's pixels
+  {
+    const int obw = TW < 32 ? TW : 32, obh = 32 / obw;
+    const int flow2 = d.epilogue == RNC_EPI_RELU_FLOW ? 2 : 0;
+    const int cw = d.epilogue == RNC_EPI_GRU_ZR ? d.cout / 2 : (d.cout + flow2 + 31) / 32 * 32;
+    if (d.out_hi) {
+      if ((d.ldo_split & 7) || !aligned16(d.out_hi) || !aligned16(d.out_lo) || d.ldo_split < cw) return RNC_ERR_BAD_POINTER;
+      ok = ok && make_out_map(&maps[6], d.out_hi, cw, d.ldo_split, d.B, d.H, d.W, obw, obh, false) &&
+           make_out_map(&maps[7], d.out_lo, cw, d.ldo_split, d.B, d.H, d.W, obw, obh, false);
+    } else {
+      maps[6] = maps[0]; maps[7] = maps[0];
+    }
+    if (d.epilogue == RNC_EPI_GRU_Q) {
+      if (!aligned16(d.h) || d.ldh < d.cout) return RNC_ERR_BAD_POINTER;
+      ok = ok && make_out_map(&maps[8], d.h, d.cout, d.ldh, d.B, d.H, d.W, obw, obh, true);
+    } else {
+      maps[8] = maps[0];
+    }
+  }
   if (!ok) return RNC_ERR_BAD_SHAPE;
 
   cudaStream_t s = as_stream(stream);
