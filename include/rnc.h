@@ -33,7 +33,7 @@ typedef enum {
 } rnc_status;
 
 /* Library identity / diagnostics. */
-int rnc_abi_version(void);                 /* bumps on any signature change (now 9) */
+int rnc_abi_version(void);                 /* bumps on any signature change (now 10) */
 const char* rnc_build_info(void);          /* e.g. "sm_100a nvcc 12.9" */
 const char* rnc_status_string(int status);
 int rnc_last_cuda_error(void);             /* cudaError_t of the last failed launch on this thread */
@@ -127,6 +127,7 @@ typedef enum {
 #define RNC_CONV_OUT_BLOCKED 32     /* RNC_EPI_LINEAR: out_f32 in the same tile-blocked layout (produces an `add` operand)          */
 #define RNC_CONV_NO_PAIR 8          /* never use the CTA-pair (cta_group::2) form for this call */
 #define RNC_CONV_SPLIT_N 4          /* 256-column layers as two 128-column items per pixel tile (double-buffered TMEM) */
+#define RNC_CONV_WINDOW 128        /* in0 is a sliding-window view of a padded plane, see rnc_conv_umma_desc.win_pitch */
 #define RNC_CONV_TF32 64            /* operands are fp32 hi/lo planes consumed as TF32 (tcgen05 kind::tf32, K = 8): value = hi + lo with
                                      * hi = tf32(value), 3 MMAs per K step as in the fp16 form but with fp32's exponent range — the
                                      * training path's layers (output gradients underflow the fp16 split).  The in / w pointers address float
@@ -178,6 +179,11 @@ typedef struct {
                                         * outputs, ACCUMULATED (caller keeps it zeroed: rnc_instnorm_finalize re-zeroes) */
   const float* add; int ldadd;         /* optional: fp32 [B*H*W][ldadd] added to the pre-activation (after bias), e.g. the
                                         * hoisted contribution of input channels that do not change between calls */
+  int win_pitch;                       /* RNC_CONV_WINDOW (kw = 1, stride 2, c1 = 0): position x of input row y exposes the c0
+                                        * consecutive halves that start at element y*win_pitch + x*ld0 of in0 (ld0 < c0: the
+                                        * windows overlap; the TMA unit builds the im2col rows); win = positions per row (one
+                                        * per output column), hin = rows, the stride applies to rows only. Used by the encoders'
+                                        * 7x7/2 stem: a [hin][win_pitch/4][4] zero-padded pixel plane, 16-pixel windows, ld0 = 8 */
 } rnc_conv_umma_desc;
 
 /* Pixel tiles (128 output pixels each) a layer of this shape is cut into: a tile-blocked tensor with ld channels has
@@ -209,6 +215,12 @@ int rnc_conv_flow7x7_fwd(const float* coords1, const float* weight, const float*
  * as fp32 and/or split halves; relu != 0 applies ReLU (norm folded into the weights). */
 int rnc_stem_conv7x7s2_fwd(const float* img, const float* weight, const float* bias, int N, int Hin, int Win, int relu,
                            float* out_f32, void* out_hi, void* out_lo, void* stream);
+/* The same layer on the tensor cores: this call normalises the image and repacks it as a zero-padded pixel plane of split
+ * halves [N][Hin][pitch_px][4] (pixel p = image column p - 3, channel 3 = 0; pitch_px even, >= Win + 6; the caller keeps
+ * >= 16 zero pixels after the last row); rnc_conv2d_umma_fwd then reads it as a sliding-window view (RNC_CONV_WINDOW:
+ * c0 = 64 = 16 pixels x 4, ld0 = 8, win_pitch = 4*pitch_px, kh = 7, kw = 1, stride 2) with the 7x7x3 filter laid out as
+ * [64][7 rows][16 px x 4 ch] (zeros for px >= 7 and channel 3): the TMA unit builds the im2col rows, no copy. */
+int rnc_stem_window_prep(const float* img, int N, int Hin, int Win, int pitch_px, void* out_hi, void* out_lo, void* stream);
 /* nn.InstanceNorm2d (no affine, biased variance; extractor.py:28-33,128-129) statistics of x CL fp32 [N][P][C], C <= 128:
  * stats = fp64 scratch [N][C][2]; mean_rstd = [N][C][2] floats (mean, 1/sqrt(var+eps)). */
 int rnc_instnorm_stats(const float* x, int N, int P, int C, float eps, double* stats, float* mean_rstd, void* stream);

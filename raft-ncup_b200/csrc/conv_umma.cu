@@ -32,7 +32,8 @@ enum { MODE_TAP = 0, MODE_ROWHALO = 1, MODE_COLHALO = 2 };
 struct Params {
   int B, H, W;                        // output geometry
   int TW, TH, tiles_x, tiles_y, ntiles, ntn;
-  int mode, kh, kw, ph, pw, stride;
+  int mode, kh, kw, ph, pw, stride;   // stride: y (and x unless sx overrides)
+  int sx;                             // x stride (1 for a window view, whose positions already step by the stride)
   int nblk0, nblk;                    // K blocks (128 bytes of channels: 64 halves or 32 TF32 words) in segment 0 / total
   int bk;                             // channels per K block: 64 (fp16 hi/lo operands) or 32 (TF32 hi/lo operands)
   int tf32;                           // operands are fp32 planes consumed as TF32 (kind::tf32): training-path layers
@@ -165,7 +166,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
         const int y0 = (tr / p.tiles_x) * p.TH, x0 = (tr % p.tiles_x) * p.TW;
         for (int g = 0; g < G; ++g) {
           int cx, cy;
-          if (p.mode == MODE_TAP) { cx = x0 * p.stride + g % p.kw - p.pw; cy = y0 * p.stride + g / p.kw - p.ph; }
+          if (p.mode == MODE_TAP) { cx = x0 * p.sx + g % p.kw - p.pw; cy = y0 * p.stride + g / p.kw - p.ph; }
           else if (p.mode == MODE_ROWHALO) { cx = x0 - p.pw; cy = y0 + g - p.ph; }
           else { cx = x0; cy = y0 - p.ph; }
           for (int cb = 0; cb < p.nblk; ++cb) {
@@ -578,12 +579,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
 // ---------------------------------------------------------------------------------------------- host side
 // activation plane [B][Hin][Win][ld] halves: 4-D map {C, Win, Hin, B}; the box spans bw x bh input elements and is
 // traversed with element strides (sx, sy) -> (bw/sx) x (bh/sy) rows of 64 channels in shared memory
-static bool make_in_map(CUtensorMap* m, const void* base, int C, int ld, int B, int Hin, int Win, int bw, int bh, int stride, bool tf32) {
+static bool make_in_map(CUtensorMap* m, const void* base, int C, int ld, int B, int Hin, int Win, int bw, int bh, int sx, int sy, bool tf32,
+                        long long row_pitch = 0) {
   const cuuint64_t esz = tf32 ? 4 : 2;                        // 128-byte rows: 32 fp32 words or 64 halves
+  const cuuint64_t pitch = row_pitch > 0 ? (cuuint64_t)row_pitch : (cuuint64_t)Win * ld;     // elements between image rows
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B};
-  const cuuint64_t strides[3] = {(cuuint64_t)ld * esz, (cuuint64_t)Win * ld * esz, (cuuint64_t)Hin * Win * ld * esz};
-  const cuuint32_t box[4] = {tf32 ? 32u : 64u, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), 1};
-  const cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  // window view (RNC_CONV_WINDOW): ld < C, i.e. consecutive positions overlap -- the TMA unit walks plain strides
+  const cuuint64_t strides[3] = {(cuuint64_t)ld * esz, pitch * esz, (cuuint64_t)Hin * pitch * esz};
+  const cuuint32_t box[4] = {tf32 ? 32u : 64u, (cuuint32_t)(bw * sx), (cuuint32_t)(bh * sy), 1};
+  const cuuint32_t es[4] = {1, (cuuint32_t)sx, (cuuint32_t)sy, 1};
   return encode_fn()(m, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -628,11 +632,11 @@ static int launch(const CUtensorMap* maps, Params& p, cudaStream_t stream, int m
   const int a_stage = 2 * p.a_plane;
   // ring depths within kRingBudget: both rings hide the same TMA latency, so deepen A (up to 4) while B keeps >= 3 stages
   const int budget = kRingBudget, b_stage = PAIR ? C::kBTile : 2 * C::kBTile;      // a pair's CTA stages half of the weight rows
+  const int sa_cap = max_sa > 0 && max_sa < kMaxSA ? max_sa : kMaxSA;      // debug knobs (rnc_conv_umma_desc.flags bits 8-15)
   p.SA = 2;
-  while (p.SA < kMaxSA && budget - (p.SA + 1) * a_stage >= 3 * b_stage) ++p.SA;
+  while (p.SA < sa_cap && budget - (p.SA + 1) * a_stage >= 3 * b_stage) ++p.SA;
   int sb = (budget - p.SA * a_stage) / b_stage;
   p.SB = sb > 8 ? 8 : sb < 2 ? 2 : sb;
-  if (max_sa > 0 && p.SA > max_sa) p.SA = max_sa;      // debug knobs (rnc_conv_umma_desc.flags bits 8-15)
   if (max_sb > 0 && p.SB > max_sb) p.SB = max_sb;
   // Small layers (64 -> 64 3x3: 9 stages of 16 KB): keep the whole weight matrix in the ring for the CTA's lifetime instead
   // of re-streaming it for every pixel tile (the shared-memory fill bandwidth is what bounds narrow tiles).
@@ -647,6 +651,7 @@ static int launch(const CUtensorMap* maps, Params& p, cudaStream_t stream, int m
   }
   // + alignment slack, barriers, fp64 statistics slots, 1024-aligned epilogue staging
   const int smem = p.SA * a_stage + p.SB * b_stage + 1024 + 512 + (BN <= 128 ? 8192 : 0) + 1024 + kStageBytes;
+  if (smem > 227 * 1024) return RNC_ERR_UNSUPPORTED;
   static unsigned long long done = 0;
   if (int st = ensure_dyn_smem(conv_umma_kernel<BN, PAIR>, 227 * 1024, &done)) return st;
   const int items = (PAIR ? (p.ntiles + 1) / 2 : p.ntiles) * p.ntn;
@@ -751,7 +756,11 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   const int bk = tf32 ? 32 : kBK, ldmask = tf32 ? 3 : 7;      // operand rows are 16-byte multiples
   if (tf32 && (d.out_hi || d.epilogue == RNC_EPI_RELU_FLOW || d.epilogue == RNC_EPI_GRU_ZR || d.epilogue == RNC_EPI_TANH_RELU))
     return RNC_ERR_UNSUPPORTED;                                // TF32 layers write fp32 outputs only
-  if ((d.ld0 & ldmask) || d.ld0 < d.c0 || (d.c1 > 0 && ((d.c0 % bk) != 0 || (d.ld1 & ldmask) || d.ld1 < d.c1))) return RNC_ERR_BAD_SHAPE;
+  const bool window = (d.flags & RNC_CONV_WINDOW) != 0;
+  if (window && (tf32 || d.c1 > 0 || d.kw != 1 || stride != 2 || d.win <= 0 || d.hin <= 0 || d.win_pitch < d.win * d.ld0 ||
+                 (d.win_pitch & 7)))
+    return RNC_ERR_BAD_SHAPE;
+  if ((d.ld0 & ldmask) || (d.ld0 < d.c0 && !window) || (d.c1 > 0 && ((d.c0 % bk) != 0 || (d.ld1 & ldmask) || d.ld1 < d.c1))) return RNC_ERR_BAD_SHAPE;
   if (!d.in0_hi || !d.in0_lo || (d.c1 > 0 && (!d.in1_hi || !d.in1_lo)) || !d.w_hi || !d.w_lo || !d.bias) return RNC_ERR_BAD_POINTER;
   if (!aligned16(d.in0_hi) || !aligned16(d.in0_lo) || !aligned16(d.w_hi) || !aligned16(d.w_lo) || !aligned16(d.bias)) return RNC_ERR_BAD_POINTER;
   if (d.c1 > 0 && (!aligned16(d.in1_hi) || !aligned16(d.in1_lo))) return RNC_ERR_BAD_POINTER;
@@ -761,6 +770,8 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   int bn;
   if (d.coutpad <= 32) bn = 32; else if (d.coutpad <= 64) bn = 64; else if (d.coutpad <= 128) bn = 128;
   else if (d.coutpad % 192 == 0) bn = 192; else bn = 256;
+  // a single CTA stages whole weight tiles: two 64 KB stages of a 256-column tile no longer fit beside the epilogue staging
+  if (bn == 256 && !(umma::pair_enabled() && (d.flags & RNC_CONV_NO_PAIR) == 0)) bn = 128;
   if (d.coutpad % bn == 0 && d.epilogue != RNC_EPI_RELU_FLOW && d.epilogue != RNC_EPI_FLOW_DELTA)
     bn = choose_bn(d, bn, stride);
   if (d.coutpad % bn != 0 || d.coutpad < d.cout) return RNC_ERR_BAD_SHAPE;
@@ -798,7 +809,7 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   // ---- tile shape and A-staging mode
   Params p;
   p.B = d.B; p.H = d.H; p.W = d.W;
-  p.kh = d.kh; p.kw = d.kw; p.ph = d.kh / 2; p.pw = d.kw / 2; p.stride = stride;
+  p.kh = d.kh; p.kw = d.kw; p.ph = d.kh / 2; p.pw = d.kw / 2; p.stride = stride; p.sx = window ? 1 : stride;
   int mode = MODE_TAP;
   if (stride == 1 && (d.flags & RNC_CONV_NO_HALO) == 0) {
     if (d.kw > 1 && d.W > 64) mode = MODE_ROWHALO;                 // one image row x 128 px per tile
@@ -837,11 +848,12 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   if (p.aux_blocked && d.epilogue != RNC_EPI_GRU_ZR && d.epilogue != RNC_EPI_GRU_Q) return RNC_ERR_UNSUPPORTED;
 
   CUtensorMap maps[9];
-  bool ok = make_in_map(&maps[0], d.in0_hi, d.c0, d.ld0, d.B, Hin, Win, box_w, box_h, stride, tf32) &&
-            make_in_map(&maps[1], d.in0_lo, d.c0, d.ld0, d.B, Hin, Win, box_w, box_h, stride, tf32);
+  const long long pitch0 = window ? d.win_pitch : 0;
+  bool ok = make_in_map(&maps[0], d.in0_hi, d.c0, d.ld0, d.B, Hin, Win, box_w, box_h, p.sx, stride, tf32, pitch0) &&
+            make_in_map(&maps[1], d.in0_lo, d.c0, d.ld0, d.B, Hin, Win, box_w, box_h, p.sx, stride, tf32, pitch0);
   if (d.c1 > 0) {
-    ok = ok && make_in_map(&maps[2], d.in1_hi, d.c1, d.ld1, d.B, Hin, Win, box_w, box_h, stride, tf32) &&
-         make_in_map(&maps[3], d.in1_lo, d.c1, d.ld1, d.B, Hin, Win, box_w, box_h, stride, tf32);
+    ok = ok && make_in_map(&maps[2], d.in1_hi, d.c1, d.ld1, d.B, Hin, Win, box_w, box_h, stride, stride, tf32) &&
+         make_in_map(&maps[3], d.in1_lo, d.c1, d.ld1, d.B, Hin, Win, box_w, box_h, stride, stride, tf32);
   } else {
     maps[2] = maps[0]; maps[3] = maps[1];
   }

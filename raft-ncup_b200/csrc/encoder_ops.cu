@@ -239,6 +239,33 @@ __global__ void pool2_cl_kernel2(const float4* __restrict__ src, float4* __restr
   }
 }
 
+
+// Image normalisation 2*(x/255)-1 (raft_nc_dbl.py:118-119) + repack for the tensor-core stem (rnc_conv_umma_desc.win_pitch):
+// NCHW fp32 -> zero-padded pixel plane [N][Hin][pitch_px][4] of split halves; pixel p holds image column p - 3 (channels
+// 0..2, channel 3 = 0), zero outside the image, so that output column ox's 7 taps start at pixel 2*ox: a 16-byte step.
+__global__ void __launch_bounds__(256)
+stem_window_prep_kernel(const float* __restrict__ img, int N, int Hin, int Win, int pitch_px, uint2* __restrict__ hi,
+                        uint2* __restrict__ lo) {
+  const size_t total = static_cast<size_t>(N) * Hin * pitch_px;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int p = static_cast<int>(i % pitch_px);
+    const size_t row = i / pitch_px;                       // n * Hin + y
+    const int x = p - 3;
+    float v[3] = {0.f, 0.f, 0.f};
+    if (x >= 0 && x < Win) {
+      const size_t n = row / Hin, y = row - n * Hin;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        v[c] = __fsub_rn(__fmul_rn(2.f, __fdiv_rn(img[((n * 3 + c) * Hin + y) * Win + x], 255.f)), 1.f);
+    }
+    uint2 h, l;
+    split_pair(v[0], v[1], h.x, l.x);
+    split_pair(v[2], 0.f, h.y, l.y);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
 }  // namespace rnc
 
 using namespace rnc;
@@ -256,6 +283,16 @@ int rnc_stem_conv7x7s2_fwd(const float* img, const float* weight, const float* b
   if (int st = ensure_dyn_smem(stem_conv7x7s2_kernel, ST_SMEM, &done)) return st;
   stem_conv7x7s2_kernel<<<grid, 256, ST_SMEM, as_stream(stream)>>>(img, weight, bias, N, Hin, Win, Ho, Wo, relu, out_f32,
                                                             static_cast<__half*>(out_hi), static_cast<__half*>(out_lo));
+  return after_launch();
+}
+
+int rnc_stem_window_prep(const float* img, int N, int Hin, int Win, int pitch_px, void* out_hi, void* out_lo, void* stream) {
+  if (N <= 0 || Hin <= 0 || Win <= 0 || pitch_px < Win + 6 || (pitch_px & 1)) return RNC_ERR_BAD_SHAPE;
+  if (!img || !out_hi || !out_lo || !aligned16(out_hi) || !aligned16(out_lo)) return RNC_ERR_BAD_POINTER;
+  const size_t total = static_cast<size_t>(N) * Hin * pitch_px;
+  const int blocks = static_cast<int>(total / 256 < 148 * 16 ? total / 256 + 1 : 148 * 16);
+  stem_window_prep_kernel<<<blocks, 256, 0, as_stream(stream)>>>(img, N, Hin, Win, pitch_px, static_cast<uint2*>(out_hi),
+                                                                  static_cast<uint2*>(out_lo));
   return after_launch();
 }
 

@@ -1,7 +1,9 @@
 """fnet / cnet (core/extractor.py:118-192 BasicEncoder, ResidualBlock :6-56) on the tensor-core convolution path.
 
-The wide 3x3 / 1x1 layers run on rnc_conv2d_umma_fwd (fp16 hi/lo split operands, stride 1/2); the 7x7 stem (K = 147) is an
-exact fp32 kernel fused with the image normalisation; InstanceNorm (fnet) is a statistics pass + an apply pass fused with
+The wide 3x3 / 1x1 layers run on rnc_conv2d_umma_fwd (fp16 hi/lo split operands, stride 1/2); so does the 7x7/2 stem: the
+normalised image is repacked once as a zero-padded [H][W+8][4] plane of split halves and the convolution reads it through a
+sliding-window tensor map (16-pixel windows 16 bytes apart: the TMA unit builds the im2col rows; 7 row taps x 64 = K 448 with
+zero weights for the 9 phantom pixels and the phantom channel); InstanceNorm (fnet) is a statistics pass + an apply pass fused with
 ReLU / residual add / re-splitting; BatchNorm (cnet, eval mode) is folded into the convolution weights.  The encoders write
 their results straight into the loop's resident buffers: fmap1 -> f1_cl, fmap2 -> level 0 of f2_pyr, tanh(net) -> h and
 hx[:, 0:128], relu(inp) -> hx[:, 128:256] (raft_nc_dbl.py:129-140).
@@ -36,8 +38,10 @@ class PackedEncoder:
         if bn and any(m.training for m in enc.modules() if isinstance(m, torch.nn.BatchNorm2d)):
             raise NotImplementedError("cnet BatchNorm in training mode (batch statistics) is not built; call .eval() / freeze_bn()")
         w, b = _fold_bn(enc.conv1, enc.norm1 if bn else None)
-        self.stem_w = w.permute(1, 2, 3, 0).reshape(147, 64).contiguous()
-        self.stem_b = b.contiguous()
+        # window form of the 7x7x3 filter: input "channel" e = 4 * px + c of the 16-pixel window, one tap per filter row
+        wv = torch.zeros(w.shape[0], 16, 4, 7, dtype=torch.float32, device=w.device)
+        wv[:, :7, :3, :] = w.permute(0, 3, 1, 2)              # [o][kx][c][ky]
+        self.stem = UmmaWeights(wv.reshape(w.shape[0], 64, 7, 1), b, [64])
         self.blocks = []
         for layer in (enc.layer1, enc.layer2, enc.layer3):
             for blk in layer:
@@ -71,6 +75,11 @@ class EncoderBuffers:
             self.D32.append(torch.empty(rows, c, **f) if c != 64 else None)
             self.XS.append(SplitBuf(rows, c, device))
             self.AS.append(SplitBuf(rows, c, device))
+        # stem input: zero-padded pixel plane [N][Hin][pitch][4] of split halves (+ 32 zero pixels: the last windows run over)
+        self.pitch = (Win + 7) & ~1
+        npx = N * Hin * self.pitch + 32
+        self.img_hi = torch.zeros(npx, 4, dtype=torch.float16, device=device)
+        self.img_lo = torch.zeros(npx, 4, dtype=torch.float16, device=device)
         self.stats = torch.zeros(N * 128 * 2, dtype=torch.float64, device=device)   # kept zeroed by rnc_instnorm_finalize
         self.mr = torch.empty(N * 128 * 2, **f)
 
@@ -107,13 +116,17 @@ class EncoderRunner:
         E, eng, s = native, self.eng, _stream()
         inst = pk.kind == "instance"
         h, w, _ = bufs.dims[0]
+        native.check(self.L.rnc_stem_window_prep(_ptr(image), N, Hin, Win, bufs.pitch, _ptr(bufs.img_hi), _ptr(bufs.img_lo), s),
+                     "stem_window_prep")
+        win = dict(stride=2, hin=Hin, win=w, win_pitch=4 * bufs.pitch, flags=eng.conv_flags | E.CONV_WINDOW)
+        img = (bufs.img_hi.data_ptr(), bufs.img_lo.data_ptr())
         if inst:
-            native.check(self.L.rnc_stem_conv7x7s2_fwd(_ptr(image), _ptr(pk.stem_w), _ptr(pk.stem_b), N, Hin, Win, 0, _ptr(bufs.T32[0]),
-                                                       C.c_void_p(0), C.c_void_p(0), s), "stem")
-            self._norm(bufs, bufs.T32[0], N, h * w, 64, 1, out32=bufs.X32[0], split=bufs.XS[0])
+            eng.uconv(N, h, w, img, 64, 8, pk.stem, E.EPI_LINEAR, out_f32=bufs.T32[0].data_ptr(), ldo_f32=64,
+                      stats=bufs.stats.data_ptr(), **win)
+            self._norm(bufs, bufs.T32[0], N, h * w, 64, 1, out32=bufs.X32[0], split=bufs.XS[0], fused_stats=True)
         else:
-            native.check(self.L.rnc_stem_conv7x7s2_fwd(_ptr(image), _ptr(pk.stem_w), _ptr(pk.stem_b), N, Hin, Win, 1, _ptr(bufs.X32[0]),
-                                                       _ptr(bufs.XS[0].hi), _ptr(bufs.XS[0].lo), s), "stem")
+            eng.uconv(N, h, w, img, 64, 8, pk.stem, E.EPI_RELU, out_f32=bufs.X32[0].data_ptr(), ldo_f32=64,
+                      out_split=bufs.XS[0].ptrs(), ldo_split=64, **win)
         lvl = 0
         for (cin, cout, stride, w1, w2, wd) in pk.blocks:
             src = lvl

@@ -210,12 +210,13 @@ class UmmaEngine(Engine):
 
     # ------------------------------------------------------------------ one tensor-core convolution
     def uconv(self, B, H, W, in0, c0, ld0, wt, epi, out_f32=0, ldo_f32=0, out_split=(0, 0), ldo_split=0, in1=(0, 0), c1=0, ld1=0,
-              h=0, ldh=0, aux0=0, ldaux=0, stride=1, hin=0, win=0, res=0, ldres=0, flags=None, stats=0, add=0, ldadd=0):
+              h=0, ldh=0, aux0=0, ldaux=0, stride=1, hin=0, win=0, res=0, ldres=0, flags=None, stats=0, add=0, ldadd=0, win_pitch=0):
         """One rnc_conv2d_umma_fwd call.  H, W are the OUTPUT dims; for stride 2 pass the input dims as hin, win."""
         d = UmmaConvDesc()
         d.stride, d.hin, d.win, d.res, d.ldres = stride, hin, win, res, ldres
         d.stats = stats
         d.add, d.ldadd = add, ldadd
+        d.win_pitch = win_pitch
         d.flags = self.conv_flags if flags is None else flags
         d.in0_hi, d.in0_lo, d.c0, d.ld0 = in0[0], in0[1], c0, ld0
         d.in1_hi, d.in1_lo, d.c1, d.ld1 = in1[0], in1[1], c1, ld1

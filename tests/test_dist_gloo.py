@@ -96,7 +96,8 @@ def _train_worker(rank, world, port, q):
         net = DDP(_TinyFlowNet())
         opt, sched = fetch_optimizer(net, lr=1e-2, num_steps=10)
         loss, _ = train_step(net, opt, sched, im1[lo:hi], im2[lo:hi], gt[lo:hi], valid[lo:hi], iters=3, clip=1.0)
-        q.put((rank, [p.detach().clone() for p in net.module.parameters()], float(loss)))
+        # plain lists: a tensor in the queue is shared through a file descriptor that dies with this process
+        q.put((rank, [p.detach().tolist() for p in net.module.parameters()], float(loss)))
     finally:
         dist.destroy_process_group()
 
@@ -124,5 +125,6 @@ def test_train_step_under_ddp_equals_the_full_batch_step():
     opt, sched = fetch_optimizer(net, lr=1e-2, num_steps=10)
     train_step(net, opt, sched, im1, im2, gt, valid, iters=3, clip=1.0)
     for a, b, c in zip(res[0][1], res[1][1], net.parameters()):
+        a, b = torch.tensor(a), torch.tensor(b)
         assert torch.equal(a, b)                                  # replicas in sync
         assert torch.allclose(a, c.detach(), atol=1e-6)           # == full-batch step
