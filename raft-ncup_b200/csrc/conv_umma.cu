@@ -101,7 +101,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
                  const __grid_constant__ CUtensorMap mA1h, const __grid_constant__ CUtensorMap mA1l,
                  const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl,
                  const __grid_constant__ CUtensorMap mOh, const __grid_constant__ CUtensorMap mOl,
-                 const __grid_constant__ CUtensorMap mHf, const Params p) {
+                 const __grid_constant__ CUtensorMap mOf, const Params p) {
   using C = Cfg<BN>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -356,7 +356,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
       }
       stg_busy = true;
     };
-    auto store_h = [&](const float* v, int ch) {               // fp32 v[0..32) -> channels [ch, ch+32) of h
+    auto store_f32 = [&](const float* v, int ch) {             // fp32 v[0..32) -> channels [ch, ch+32) of h (q gate) / out_f32
       stage_free();
       float4* sf = reinterpret_cast<float4*>(stg + lane * 128);
       const int sw = lane & 7;
@@ -364,7 +364,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
       for (int q = 0; q < 8; ++q) sf[q ^ sw] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { tma_store_4d(&mHf, stg, ch, bx, by, bb); bulk_commit(); }
+      if (lane == 0) { tma_store_4d(&mOf, stg, ch, bx, by, bb); bulk_commit(); }
       stg_busy = true;
     };
     int t_it = 0;
@@ -502,7 +502,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
             v[4 * q + 2] = (1.f - z.z) * hv.z + z.z * tanh_fast(v[4 * q + 2]);
             v[4 * q + 3] = (1.f - z.w) * hv.w + z.w * tanh_fast(v[4 * q + 3]);
           }
-          store_h(v, n);
+          store_f32(v, n);
         } else if (epi == RNC_EPI_RELU || epi == RNC_EPI_RELU_FLOW) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -544,15 +544,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
             want_f32 = false;
           }
         }
-        if (want_f32 && valid) {
+        if (want_f32) {
           if (p.out_blocked) {
-            float* dst = p.out_f32 + (static_cast<size_t>(tile) * p.ldo_f32 + n) * kBM + ml;
+            if (valid) {
+              float* dst = p.out_f32 + (static_cast<size_t>(tile) * p.ldo_f32 + n) * kBM + ml;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(j) * kBM] = v[j];
+              for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(j) * kBM] = v[j];
+            }
           } else {
-            float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.ldo_f32 + n);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            store_f32(v, n);
           }
         }
         if (p.out_hi) store_split(v, n);
@@ -873,8 +873,12 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
       maps[6] = maps[0]; maps[7] = maps[0];
     }
     if (d.epilogue == RNC_EPI_GRU_Q) {
-      if (!aligned16(d.h) || d.ldh < d.cout) return RNC_ERR_BAD_POINTER;
+      if (!aligned16(d.h) || d.ldh < d.cout || d.out_f32) return RNC_ERR_BAD_POINTER;
       ok = ok && make_out_map(&maps[8], d.h, d.cout, d.ldh, d.B, d.H, d.W, obw, obh, true);
+    } else if (d.out_f32 && !p.out_blocked && d.epilogue != RNC_EPI_FLOW_DELTA) {
+      const int cf = d.epilogue == RNC_EPI_TANH_RELU ? d.cout / 2 : (d.cout + 31) / 32 * 32;   // TANH_RELU: only the tanh half
+      if (d.ldo_f32 < cf) return RNC_ERR_BAD_SHAPE;
+      ok = ok && make_out_map(&maps[8], d.out_f32, cf, d.ldo_f32, d.B, d.H, d.W, obw, obh, true);
     } else {
       maps[8] = maps[0];
     }
