@@ -1,5 +1,3 @@
-export RNC_GRAPH=0
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/enc_launches.csv python tools/enc_launches.py > gpurun_out/enc.log 2>&1
-tail -3 gpurun_out/enc.log
-python tools/step_breakdown.py
+(python tools/l1_probe.py; timeout 900 python -m pytest tests/test_gpu_encoder.py tests/test_gpu_umma.py tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -5; RNC_GRAPH=0 python tools/step_breakdown.py) > gpurun_out/l1.log 2>&1
+cat gpurun_out/l1.log
