@@ -43,6 +43,62 @@ def test_stem_conv_matches_torch(Hin, Win, relu):
     assert ((hi.float() + lo.float()) - out).abs().max() < 1e-6
 
 
+@pytest.mark.parametrize("Hin,Win,inst", [(128, 256, True), (46, 70, False), (33, 41, True), (440, 1024, False)])
+def test_window_stem_matches_torch(Hin, Win, inst):
+    """The product's stem: image repacked as a zero-padded pixel plane, convolved on the tensor cores through the sliding-window
+    tensor map (rnc_conv_umma_desc.win_pitch), with the InstanceNorm sums fused (fnet) or ReLU + split output (cnet), against
+    F.conv2d in fp64 (extractor.py:135,171; raft_nc_dbl.py:118-119).  Odd sizes exercise the right / bottom borders."""
+    from rnc import native
+    from rnc.encoder_umma import EncoderBuffers, EncoderRunner, PackedEncoder
+    from rnc.engine import engine_for
+    from rnc.modules import BasicEncoder
+    torch.manual_seed(Hin + Win)
+    N = 2
+    enc = BasicEncoder(output_dim=256, norm_fn="instance" if inst else "batch", dropout=0.0).eval()
+    with torch.no_grad():
+        enc.conv1.weight.mul_(3.0)
+        enc.conv1.bias.uniform_(-1, 1)
+        if not inst:
+            enc.norm1.running_mean.uniform_(-0.2, 0.2)
+            enc.norm1.running_var.uniform_(0.5, 2.0)
+            enc.norm1.weight.uniform_(0.5, 1.5)
+            enc.norm1.bias.uniform_(-0.3, 0.3)
+    img = torch.rand(N, 3, Hin, Win) * 255
+    with torch.no_grad():
+        x = (2 * (img.double() / 255.0) - 1.0)
+        y = F.conv2d(x, enc.conv1.weight.double(), enc.conv1.bias.double(), stride=2, padding=3)
+        ref = y if inst else F.relu(F.batch_norm(y, enc.norm1.running_mean.double(), enc.norm1.running_var.double(),
+                                                 enc.norm1.weight.double(), enc.norm1.bias.double(), False, 0.0, enc.norm1.eps))
+    Ho, Wo = ref.shape[-2:]
+    eng = engine_for(torch.device(DEV))
+    enc = enc.to(DEV)
+    pk = PackedEncoder(enc)
+    bufs = EncoderBuffers(DEV, N, Hin, Win)
+    L, E = native.lib(), native
+    imgd = img.to(DEV)
+    native.check(L.rnc_stem_window_prep(P(imgd), N, Hin, Win, bufs.pitch, P(bufs.img_hi), P(bufs.img_lo), S()))
+    plane = (bufs.img_hi.float() + bufs.img_lo.float())[:N * Hin * bufs.pitch].view(N, Hin, bufs.pitch, 4).cpu()
+    want = torch.zeros(N, Hin, bufs.pitch, 4, dtype=torch.float64)
+    want[:, :, 3:3 + Win, :3] = x.permute(0, 2, 3, 1)
+    assert (plane.double() - want).abs().max() < 1e-6                  # split halves reproduce the normalised image, zero border
+    win = dict(stride=2, hin=Hin, win=Wo, win_pitch=4 * bufs.pitch, flags=eng.conv_flags | E.CONV_WINDOW)
+    ptrs = (bufs.img_hi.data_ptr(), bufs.img_lo.data_ptr())
+    out = torch.zeros(N * Ho * Wo, 64, device=DEV)
+    if inst:
+        eng.uconv(N, Ho, Wo, ptrs, 64, 8, pk.stem, E.EPI_LINEAR, out_f32=out.data_ptr(), ldo_f32=64, stats=bufs.stats.data_ptr(), **win)
+        sums = bufs.stats[:N * 64 * 2].view(N, 64, 2).cpu()
+        assert torch.allclose(sums[..., 0], ref.sum((2, 3)), rtol=1e-5, atol=1e-2)
+        assert torch.allclose(sums[..., 1], (ref * ref).sum((2, 3)), rtol=1e-5, atol=1e-2)
+    else:
+        sp_hi = torch.zeros(N * Ho * Wo, 64, dtype=torch.float16, device=DEV)
+        sp_lo = torch.zeros_like(sp_hi)
+        eng.uconv(N, Ho, Wo, ptrs, 64, 8, pk.stem, E.EPI_RELU, out_f32=out.data_ptr(), ldo_f32=64,
+                  out_split=(sp_hi.data_ptr(), sp_lo.data_ptr()), ldo_split=64, **win)
+        assert ((sp_hi.float() + sp_lo.float()) - out).abs().max() < 1e-5
+    got = out.view(N, Ho, Wo, 64).permute(0, 3, 1, 2).cpu().double()
+    assert (got - ref).abs().max() < 3e-5 * max(1.0, float(ref.abs().max()))
+
+
 @pytest.mark.parametrize("Cc,mode", [(64, 1), (96, 0), (128, 2)])
 def test_instance_norm_matches_torch(Cc, mode):
     from rnc import native
