@@ -128,7 +128,9 @@ class EncoderRunner:
             eng.uconv(N, h, w, img, 64, 8, pk.stem, E.EPI_RELU, out_f32=bufs.X32[0].data_ptr(), ldo_f32=64,
                       out_split=bufs.XS[0].ptrs(), ldo_split=64, **win)
         lvl = 0
-        for (cin, cout, stride, w1, w2, wd) in pk.blocks:
+        for bi, (cin, cout, stride, w1, w2, wd) in enumerate(pk.blocks):
+            # the fp32 copy of a block's output is only read as the next block's residual (blocks without a downsample branch)
+            need32 = bi + 1 < len(pk.blocks) and pk.blocks[bi + 1][5] is None
             src = lvl
             if stride == 2:
                 lvl += 1
@@ -149,7 +151,8 @@ class EncoderRunner:
                     res = bufs.D32[lvl]
                 eng.uconv(N, h, w, bufs.AS[lvl].ptrs(), cout, cout, w2, E.EPI_LINEAR, out_f32=bufs.T32[lvl].data_ptr(), ldo_f32=cout,
                           stats=st)
-                self._norm(bufs, bufs.T32[lvl], N, P, cout, 2, res=res, out32=bufs.X32[lvl], split=bufs.XS[lvl], fused_stats=True)
+                self._norm(bufs, bufs.T32[lvl], N, P, cout, 2, res=res, out32=bufs.X32[lvl] if need32 else None, split=bufs.XS[lvl],
+                           fused_stats=True)
             else:
                 eng.uconv(N, h, w, xs_in.ptrs(), cin, cin, w1, E.EPI_RELU, out_split=bufs.AS[lvl].ptrs(), ldo_split=cout,
                           stride=stride, hin=hi_, win=wi_)
@@ -158,8 +161,9 @@ class EncoderRunner:
                     eng.uconv(N, h, w, xs_in.ptrs(), cin, cin, wd, E.EPI_LINEAR, out_f32=bufs.D32[lvl].data_ptr(), ldo_f32=cout,
                               stride=stride, hin=hi_, win=wi_)
                     res = bufs.D32[lvl]
-                eng.uconv(N, h, w, bufs.AS[lvl].ptrs(), cout, cout, w2, E.EPI_RELU_ADD_RELU, out_f32=bufs.X32[lvl].data_ptr(),
-                          ldo_f32=cout, out_split=bufs.XS[lvl].ptrs(), ldo_split=cout, res=res.data_ptr(), ldres=cout)
+                eng.uconv(N, h, w, bufs.AS[lvl].ptrs(), cout, cout, w2, E.EPI_RELU_ADD_RELU,
+                          out_f32=bufs.X32[lvl].data_ptr() if need32 else 0, ldo_f32=cout, out_split=bufs.XS[lvl].ptrs(),
+                          ldo_split=cout, res=res.data_ptr(), ldres=cout)
         return bufs.dims[2]
 
     # ------------------------------------------------------------------ public
