@@ -68,19 +68,6 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// Sum over the warp of v[j] per j, by halving exchanges (31 shuffles): on return lane l holds the total of element l in v[0].
-__device__ __forceinline__ void warp_transpose_sum(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float send = up ? v[i] : v[i + off], keep = up ? v[i + off] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-}
-
 template <int BN>
 struct Cfg {
   static constexpr int kBTile = BN * kBK * 2;                     // bytes per half-plane of weights
@@ -419,16 +406,28 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
           }
         }
         if (use_stats) {
-          // InstanceNorm statistics of this layer's output (extractor.py:128-129), fused here instead of a pass over the
-          // fp32 tensor: fp32 partial sums over the warp's 32 pixels, accumulated in fp64 per lane (= channel) in shared
-          // memory across the CTA's tiles and flushed with fp64 atomics when the image changes
-          float s1[32], s2[32];
+          // InstanceNorm statistics of this layer's output (extractor.py:128-129), fused here instead of a pass over the fp32
+          // tensor.  The chunk is staged in shared memory for its TMA store anyway ([pixel][32 ch], 128B-swizzled), which is
+          // the transposition the reduction over pixels needs: lane = channel walks its column (conflict-free: a row's 32
+          // words are a permutation of the 32 banks), fp32 partial sums over the warp's 32 pixels, accumulated in fp64 per
+          // lane in shared memory across the CTA's tiles and flushed with fp64 atomics when the image changes.  Pixels beyond
+          // the image are staged as zeros (the TMA store clips them).
+          if (!valid) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { s1[j] = valid ? v[j] : 0.f; s2[j] = s1[j] * s1[j]; }
-          warp_transpose_sum(s1, lane);
-          warp_transpose_sum(s2, lane);
-          my_acc[(cc - cc0) * 64] += static_cast<double>(s1[0]);
-          my_acc[(cc - cc0) * 64 + 1] += static_cast<double>(s2[0]);
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          store_f32(v, n);                       // stats layers are RNC_EPI_LINEAR with a channel-last fp32 output (host check)
+          float s1 = 0.f, s2 = 0.f;
+          const int cw = lane >> 2, ce = lane & 3;
+#pragma unroll
+          for (int px = 0; px < 32; ++px) {
+            const float x = *reinterpret_cast<const float*>(stg + px * 128 + ((cw ^ (px & 7)) << 4) + ce * 4);
+            s1 += x;
+            s2 = fmaf(x, x, s2);
+          }
+          my_acc[(cc - cc0) * 64] += static_cast<double>(s1);
+          my_acc[(cc - cc0) * 64 + 1] += static_cast<double>(s2);
+          continue;
         }
         if (epi == RNC_EPI_GRU_ZR) {
           const int Ch = p.cout >> 1;
@@ -779,7 +778,7 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   if (d.out_hi && (!d.out_lo || (d.ldo_split & 7) || !aligned16(d.out_hi) || !aligned16(d.out_lo))) return RNC_ERR_BAD_POINTER;
   if (d.out_f32 && ((d.ldo_f32 & 3) || !aligned16(d.out_f32))) return RNC_ERR_BAD_POINTER;
   if (d.add && ((d.ldadd & 3) || d.ldadd < d.coutpad || !aligned16(d.add))) return RNC_ERR_BAD_POINTER;
-  if (d.stats && (d.epilogue != RNC_EPI_LINEAR || !d.out_f32 || d.coutpad > 128)) return RNC_ERR_UNSUPPORTED;
+  if (d.stats && (d.epilogue != RNC_EPI_LINEAR || !d.out_f32 || d.out_hi || d.coutpad > 128)) return RNC_ERR_UNSUPPORTED;
   switch (d.epilogue) {
     case RNC_EPI_RELU_ADD_RELU:
       if (!d.res || (d.ldres & 3) || !aligned16(d.res)) return RNC_ERR_BAD_POINTER;
