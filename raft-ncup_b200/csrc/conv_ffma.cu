@@ -87,11 +87,13 @@ conv_cl_ffma_kernel(const ConvParams p) {
   };
 
   const int tx = tid & 7, ty = tid >> 3;
-  float acc[8][8];
+  // accumulators as pairs of adjacent output columns: one packed FFMA2 (fma.rn.f32x2) per pair halves the FMA instruction
+  // count of the 8x8 micro tile (same IEEE fma per element: bit-identical to the scalar form)
+  float2 acc2[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc2[i][j] = make_float2(0.f, 0.f);
 
   load_chunk(0);
   store_chunk(0);
@@ -106,11 +108,13 @@ conv_cl_ffma_kernel(const ConvParams p) {
       const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 8]);
       const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 8 + 4]);
       const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float2 bv2[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i) {
+        const float2 ai = make_float2(av[i], av[i]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc2[i][j] = __ffma2_rn(ai, bv2[j], acc2[i][j]);
+      }
     }
     if (kc + 1 < nchunks) store_chunk(buf ^ 1);
     __syncthreads();
@@ -122,6 +126,11 @@ conv_cl_ffma_kernel(const ConvParams p) {
   float bias[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) bias[j] = d.bias[nb + j];   // bias is padded to CoutPad
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[i][2 * j] = acc2[i][j].x; acc[i][2 * j + 1] = acc2[i][j].y; }
 
 #pragma unroll
   for (int i = 0; i < 8; ++i) {

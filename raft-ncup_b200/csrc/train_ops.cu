@@ -121,11 +121,11 @@ conv_wgrad_kernel(const float* __restrict__ x, int ldx, int cin, const float* __
   const long long p0 = static_cast<long long>(blockIdx.z) * px_per_block;
   const long long p1 = p0 + px_per_block < P ? p0 + px_per_block : P;
   const int ty = tid >> 3, tx = tid & 7;        // thread = 8 (ci) x 8 (co) micro tile
-  float acc[8][8];
+  float2 acc2[8][4];                              // pairs of adjacent output channels: one packed FFMA2 per pair
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc2[i][j] = make_float2(0.f, 0.f);
   float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const bool do_bias = gb != nullptr && tap == 0 && ci0 == 0 && ty == 0;
   // staging: 16 px x 64 ch = 256 float4 per operand, 4 per thread: pixel = (tid >> 4) + 4 * i, channel quad = tid & 15.
@@ -169,10 +169,13 @@ conv_wgrad_kernel(const float* __restrict__ x, int ldx, int cin, const float* __
       const float4 g0 = *reinterpret_cast<const float4*>(&Gs[k][tx * 8]), g1 = *reinterpret_cast<const float4*>(&Gs[k][tx * 8 + 4]);
       const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
       const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float2 g2[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i) {
+        const float2 xi = make_float2(xa[i], xa[i]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xa[i], ga[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc2[i][j] = __ffma2_rn(xi, g2[j], acc2[i][j]);
+      }
       if (do_bias) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) bsum[j] += ga[j];
@@ -184,10 +187,11 @@ conv_wgrad_kernel(const float* __restrict__ x, int ldx, int cin, const float* __
   for (int i = 0; i < 8; ++i) {
     const int ci = ci0 + ty * 8 + i;
     if (ci >= cin) continue;
+    const float acc[8] = {acc2[i][0].x, acc2[i][0].y, acc2[i][1].x, acc2[i][1].y, acc2[i][2].x, acc2[i][2].y, acc2[i][3].x, acc2[i][3].y};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int co = co0 + tx * 8 + j;
-      if (co < cout && acc[i][j] != 0.f) atomicAdd(gw + (static_cast<size_t>(tap) * cin + ci) * ldw + co, acc[i][j]);
+      if (co < cout && acc[j] != 0.f) atomicAdd(gw + (static_cast<size_t>(tap) * cin + ci) * ldw + co, acc[j]);
     }
   }
   if (do_bias) {

@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-(python tools/l1_probe.py | head -3; timeout 900 python -m pytest tests/test_gpu_encoder.py tests/test_gpu_parity.py tests/test_gpu_bench_config.py -x -q -m gpu 2>&1 | tail -5; RNC_GRAPH=0 python tools/step_breakdown.py) > gpurun_out/stats2.log 2>&1
-cat gpurun_out/stats2.log
+(timeout 900 python -m pytest tests/test_gpu_train.py tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -5; python bench.py --mode train --steps 5 --warmup 3 2>&1 | tail -1 | cut -c1-400; python tools/train_profile.py 2>&1 | grep -v "^-" | cut -c1-62,140-260 | head -34) > gpurun_out/train2.log 2>&1
+cat gpurun_out/train2.log
