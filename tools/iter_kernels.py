@@ -26,7 +26,8 @@ with torch.no_grad():
 names = [r[0] for r in rec]
 # the loop's layers repeat with period = calls per iteration: find the tail period
 loop = [r for r in rec if r[0].endswith("55x128")]
-per = 11
+first = [i for i, r in enumerate(loop) if r[0] == loop[-1][0]]
+per = first[-1] - first[-2]                     # calls per iteration = distance between repeats of the last layer
 body = loop[-per * (iters - 2):]
 tot = 0.0
 for k in range(per):
