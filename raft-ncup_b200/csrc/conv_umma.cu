@@ -15,6 +15,10 @@
 //   ROWHALO  tile = 1 image row x 128 px: one (128 + 8)-row box per (ky, channel block); the kw horizontal taps are
 //            operand descriptors shifted by kx rows (descriptor base_offset carries the swizzle phase)
 //   COLHALO  kw == 1: tile = 8 x 16 px with a vertical halo, the kh taps are descriptors shifted by ky*16 rows
+// A fourth input form, RNC_CONV_WINDOW, reads in0 through a sliding-window tensor map (dimension 1 steps fewer bytes than
+// dimension 0 spans): the TMA unit builds im2col rows of a small-Cin layer (the encoders' 7x7/2 stem) without a copy.
+// Epilogue: TMEM -> registers -> per-warp swizzled staging in shared memory -> cp.async.bulk.tensor stores (split halves,
+// fp32 outputs, the GRU state); fused InstanceNorm sums read the staged chunk column-wise.
 #include "umma_ptx.cuh"
 
 namespace rnc {
