@@ -86,7 +86,13 @@ struct Cfg {
 // PAIR: two CTAs of a cluster (adjacent pixel tiles, same weights) run each MMA together (cta_group::2, M = 256): every CTA
 // stages its own A tile and HALF of the weight tile, so the shared-memory fill and operand-read traffic per SM drop by the
 // weight share — the resource that bounds the single-CTA form.  The leader (rank 0) issues all MMAs.
-template <int BN, bool PAIR>
+// EC: epilogue class, compiled separately so that a launch carries only its own epilogue code (the union of all epilogues cost
+// the gate layers instruction-cache misses — 18 % of the epilogue warps' stall samples — and registers): 0 = plain layers
+// (linear / relu / sigmoid), 1 = GRU z|r gates, 2 = GRU q, 3 = the rest (flow append, residual tail, tanh|relu head,
+// coords update, fused InstanceNorm sums).
+enum { EC_PLAIN = 0, EC_GRU_ZR = 1, EC_GRU_Q = 2, EC_MISC = 3 };
+
+template <int BN, bool PAIR, int EC>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant__ CUtensorMap mA0l,
                  const __grid_constant__ CUtensorMap mA1h, const __grid_constant__ CUtensorMap mA1l,
@@ -302,7 +308,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
     const int epi = p.epilogue;
     constexpr int kChunksN = BN / 32, kHalfN = (kChunksN + 1) / 2;
     const int cc0 = (warp - 2) < 4 ? 0 : kHalfN, cc1 = (warp - 2) < 4 ? kHalfN : kChunksN;
-    const bool use_stats = BN <= 128 && p.stats != nullptr;
+    const bool use_stats = EC == EC_MISC && BN <= 128 && p.stats != nullptr;
     double* my_acc = stat_acc + (static_cast<size_t>(warp - 2) * kHalfN * 32 + lane) * 2;   // [chunk] stride 64 doubles
     int acc_b = -1, acc_n0 = 0;
     auto flush_stats = [&]() {
@@ -379,7 +385,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
 #pragma unroll 1
       for (int cc = cc0; cc < cc1; ++cc) {
         const int n = n0 + cc * 32;
-        if (n >= p.cout + (epi == RNC_EPI_RELU_FLOW ? 2 : 0)) break;   // warp-uniform
+        if (n >= p.cout + (EC == EC_MISC && epi == RNC_EPI_RELU_FLOW ? 2 : 0)) break;   // warp-uniform
         uint32_t r[32], rc[32];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + buf * 2 * BN + cc * 32;
         tmem_ld32(taddr, r);
@@ -433,7 +439,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
           my_acc[(cc - cc0) * 64 + 1] += static_cast<double>(s2);
           continue;
         }
-        if (epi == RNC_EPI_GRU_ZR) {
+        if (EC == EC_GRU_ZR) {
           const int Ch = p.cout >> 1;
           if (n < Ch) {            // z gate -> fp32 aux buffer
             if (valid) {
@@ -463,7 +469,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
           }
           continue;
         }
-        if (epi == RNC_EPI_FLOW_DELTA) {
+        if (EC == EC_MISC && epi == RNC_EPI_FLOW_DELTA) {
           // FlowHead.conv2 + `coords1 = coords1 + delta_flow` (update.py:14, raft_nc_dbl.py:157); only channels 0,1 are real
           if (valid) {
             const int HW = p.H * p.W;
@@ -475,7 +481,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
           continue;
         }
         bool want_f32 = p.out_f32 != nullptr;
-        if (epi == RNC_EPI_GRU_Q) {
+        if (EC == EC_GRU_Q) {
           const float4* hp = reinterpret_cast<const float4*>(p.h + pix * p.ldh + n);
           float4 zreg[8], hreg[8];
           if (!valid) {
@@ -506,10 +512,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
             v[4 * q + 3] = (1.f - z.w) * hv.w + z.w * tanh_fast(v[4 * q + 3]);
           }
           store_f32(v, n);
-        } else if (epi == RNC_EPI_RELU || epi == RNC_EPI_RELU_FLOW) {
+        } else if (EC == EC_PLAIN) {
+          if (epi == RNC_EPI_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (epi == RNC_EPI_SIGMOID) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = sigmoid_fast(v[j]);
+          }
+        } else if (EC != EC_MISC) {
+          // (not reached: the z|r class left the chunk above)
+        } else if (epi == RNC_EPI_RELU_FLOW) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          if (epi == RNC_EPI_RELU_FLOW && n <= p.cout && p.cout < n + 32 && valid) {
+          if (n <= p.cout && p.cout < n + 32 && valid) {
             // append flow = coords1 - grid as channels [cout, cout+2)  (update.py:97)
             const int HW = p.H * p.W;
             const float* c1 = p.aux0 + static_cast<size_t>(b) * 2 * HW + y * p.W + x;
@@ -520,9 +536,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
               if (n + j == p.cout + 1) v[j] = fy;
             }
           }
-        } else if (epi == RNC_EPI_SIGMOID) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = sigmoid_fast(v[j]);
         } else if (epi == RNC_EPI_RELU_ADD_RELU) {
           // residual block tail (extractor.py:55): relu(x + relu(norm(conv(.)))) with the norm folded into the weights
           const float4* rp = reinterpret_cast<const float4*>(p.res + pix * p.ldres + n);
@@ -629,7 +642,7 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, int EC>
 static int launch(const CUtensorMap* maps, Params& p, cudaStream_t stream, int max_sa, int max_sb) {
   using C = Cfg<BN>;
   const int a_stage = 2 * p.a_plane;
@@ -656,7 +669,7 @@ static int launch(const CUtensorMap* maps, Params& p, cudaStream_t stream, int m
   const int smem = p.SA * a_stage + p.SB * b_stage + 1024 + 512 + (BN <= 128 ? 8192 : 0) + 1024 + kStageBytes;
   if (smem > 227 * 1024) return RNC_ERR_UNSUPPORTED;
   static unsigned long long done = 0;
-  if (int st = ensure_dyn_smem(conv_umma_kernel<BN, PAIR>, 227 * 1024, &done)) return st;
+  if (int st = ensure_dyn_smem(conv_umma_kernel<BN, PAIR, EC>, 227 * 1024, &done)) return st;
   const int items = (PAIR ? (p.ntiles + 1) / 2 : p.ntiles) * p.ntn;
   const int slots = PAIR ? sm_count() / 2 : sm_count();
   const int grid = (items < slots ? items : slots) * (PAIR ? 2 : 1);
@@ -675,10 +688,21 @@ static int launch(const CUtensorMap* maps, Params& p, cudaStream_t stream, int m
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, PAIR>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7],
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, PAIR, EC>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7],
                                      maps[8], p);
   if (e != cudaSuccess) { g_last_cuda_error = static_cast<int>(e); return RNC_ERR_CUDA; }
   return after_launch();
+}
+
+template <bool PAIR, int EC>
+static int launch_bn(int bn, const CUtensorMap* maps, Params& p, cudaStream_t s, int msa, int msb) {
+  switch (bn) {
+    case 32: return launch<32, PAIR, EC>(maps, p, s, msa, msb);
+    case 64: return launch<64, PAIR, EC>(maps, p, s, msa, msb);
+    case 128: return launch<128, PAIR, EC>(maps, p, s, msa, msb);
+    case 192: return launch<192, PAIR, EC>(maps, p, s, msa, msb);
+    default: return launch<256, PAIR, EC>(maps, p, s, msa, msb);
+  }
 }
 
 // CTA-pair (cta_group::2) form of the convolution: the default; RNC_CONV_PAIR=0 selects the single-CTA form
@@ -890,20 +914,20 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
 
   cudaStream_t s = as_stream(stream);
   const int msa = (d.flags >> 8) & 15, msb = (d.flags >> 12) & 15;
+  const bool plain = (d.epilogue == RNC_EPI_LINEAR || d.epilogue == RNC_EPI_RELU || d.epilogue == RNC_EPI_SIGMOID) && !d.stats;
+  const int ec = d.epilogue == RNC_EPI_GRU_ZR ? EC_GRU_ZR : d.epilogue == RNC_EPI_GRU_Q ? EC_GRU_Q : plain ? EC_PLAIN : EC_MISC;
   if (pair) {
-    switch (bn) {
-      case 32: return launch<32, true>(maps, p, s, msa, msb);
-      case 64: return launch<64, true>(maps, p, s, msa, msb);
-      case 128: return launch<128, true>(maps, p, s, msa, msb);
-      case 192: return launch<192, true>(maps, p, s, msa, msb);
-      default: return launch<256, true>(maps, p, s, msa, msb);
+    switch (ec) {
+      case EC_GRU_ZR: return launch_bn<true, EC_GRU_ZR>(bn, maps, p, s, msa, msb);
+      case EC_GRU_Q: return launch_bn<true, EC_GRU_Q>(bn, maps, p, s, msa, msb);
+      case EC_MISC: return launch_bn<true, EC_MISC>(bn, maps, p, s, msa, msb);
+      default: return launch_bn<true, EC_PLAIN>(bn, maps, p, s, msa, msb);
     }
   }
-  switch (bn) {
-    case 32: return launch<32, false>(maps, p, s, msa, msb);
-    case 64: return launch<64, false>(maps, p, s, msa, msb);
-    case 128: return launch<128, false>(maps, p, s, msa, msb);
-    case 192: return launch<192, false>(maps, p, s, msa, msb);
-    default: return launch<256, false>(maps, p, s, msa, msb);
+  switch (ec) {
+    case EC_GRU_ZR: return launch_bn<false, EC_GRU_ZR>(bn, maps, p, s, msa, msb);
+    case EC_GRU_Q: return launch_bn<false, EC_GRU_Q>(bn, maps, p, s, msa, msb);
+    case EC_MISC: return launch_bn<false, EC_MISC>(bn, maps, p, s, msa, msb);
+    default: return launch_bn<false, EC_PLAIN>(bn, maps, p, s, msa, msb);
   }
 }
