@@ -469,7 +469,7 @@ def run_native(args, rank, world, local_rank):
                 "d2h_bytes_per_step": int(out_lo.numel() + out_up.numel()) * 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "corr_lookup_umma_kernel (tcgen05 fused corr lookup, K2; + exact fallback launch)", "bound": "hbm",
+        "roofline": {"kernel": "corr_lookup_umma_kernel (tcgen05 fused corr lookup, K2; incoherent units recomputed exactly inside the same launch)", "bound": "hbm",
                      "achieved": k2_gbs, "peak": peak, "unit": "GB/s", "frac": k2_gbs / peak, "traffic": ncu_traffic("corr_lookup"),
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": k2_bytes,
                      "algorithmic_bytes_note": "SURVEY §8d contract figure (fp32 storage: 25,891,840 B/pair-iter); at the storage "
