@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-(for r in 1 2; do echo "--- new"; python bench.py --mode train --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['ms_per_step'], d.get('tf32x3_convs',{}).get('ms_per_step'))"; echo "--- old"; (cd _old && python bench.py --mode train --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['ms_per_step'], d.get('tf32x3_convs',{}).get('ms_per_step'))"); done) > gpurun_out/train_ab.log 2>&1
-cat gpurun_out/train_ab.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02_infer_n8.json 2> gpurun_out/r02_infer_n8.err
+tail -c 600 gpurun_out/r02_infer_n8.err; cut -c1-400 gpurun_out/r02_infer_n8.json
