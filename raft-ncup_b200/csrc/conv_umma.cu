@@ -105,7 +105,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
   const int a_stage = 2 * p.a_plane;
   unsigned char* sA = smem;
   unsigned char* sB = smem + p.SA * a_stage;
-  constexpr int kBStageBytes = PAIR ? C::kBTile : 2 * C::kBTile;      // [hi | lo] (half-)planes of one K block
+  // Pair form of narrow tiles (BN <= 64): an MMA of 64 columns is bound by the issue rate, so the two products that share x_hi
+  // become ONE instruction of 2*BN columns — the leader stages all BN rows of w_hi, its peer all BN rows of w_lo at the same
+  // offset X (a cta_group::2 MMA takes half of its N columns from each CTA: columns [0, BN) = x_hi*w_hi -> main, [BN, 2BN) =
+  // x_hi*w_lo -> corr, adjacent in TMEM) — and x_lo*w_hi reads each CTA's half of w_hi from a second region Y.
+  constexpr bool kFusedPair = PAIR && BN <= 64;
+  constexpr int kBStageBytes = kFusedPair ? C::kBTile + C::kBTile / 2 : PAIR ? C::kBTile : 2 * C::kBTile;   // weight bytes per K block and CTA
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.SB * kBStageBytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kMaxSA;
@@ -192,7 +197,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
               mbar_wait(&b_empty[sb], pb ^ 1);
               const int kcol = (tap * p.nblk + cb) * p.bk;
               if (elect_one()) {
-                if (PAIR) {                  // this CTA's half of the weight rows, hi and lo planes
+                if (kFusedPair) {            // X: all BN rows of w_hi (leader) / w_lo (peer) as two half boxes; Y: own half of w_hi
+                  const CUtensorMap* mx = leader ? &mBh : &mBl;
+                  unsigned char* st = sB + sb * kBStageBytes;
+                  if (leader) mbar_expect_tx(&b_full[sb], 2 * kBStageBytes);
+                  tma_load_2d_pair(st, mx, b_full_l + sb * 8, kcol, n0);
+                  tma_load_2d_pair(st + C::kBTile / 2, mx, b_full_l + sb * 8, kcol, n0 + BN / 2);
+                  tma_load_2d_pair(st + C::kBTile, &mBh, b_full_l + sb * 8, kcol, n0 + static_cast<int>(rank) * (BN / 2));
+                } else if (PAIR) {           // this CTA's half of the weight rows, hi and lo planes
                   const int nrow = n0 + static_cast<int>(rank) * (BN / 2);
                   if (leader) mbar_expect_tx(&b_full[sb], 2 * kBStageBytes);
                   tma_load_2d_pair(sB + sb * kBStageBytes, &mBh, b_full_l + sb * 8, kcol, nrow);
@@ -244,7 +256,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
               const uint32_t br = b_base + sb * kBStageBytes;
               const uint64_t bh = smem_desc_sw128(br), bl = smem_desc_sw128(br + kBHalf);
               if (elect_one()) {
-                if (PAIR) {
+                if (kFusedPair) {
+                  const uint64_t bx = smem_desc_sw128(br), by = smem_desc_sw128(br + C::kBTile);
+                  const uint32_t idesc_x = (1u << 4) | fmt | (static_cast<uint32_t>((2 * BN) >> 3) << 17) | (static_cast<uint32_t>((2 * kBM) >> 4) << 24);
+#pragma unroll
+                  for (int k = 0; k < kBK / 16; ++k) {
+                    if (tf32) {
+                      umma_tf32_pair(d_main, ah + 2 * k, bx + 2 * k, idesc_x, k == 0 ? acc : 1u);     // main | corr
+                      umma_tf32_pair(d_corr, al + 2 * k, by + 2 * k, idesc, 1);
+                    } else {
+                      umma_f16_pair(d_main, ah + 2 * k, bx + 2 * k, idesc_x, k == 0 ? acc : 1u);      // main | corr
+                      umma_f16_pair(d_corr, al + 2 * k, by + 2 * k, idesc, 1);
+                    }
+                  }
+                  if (!p.resident_b) umma_commit_pair(&b_empty[sb]);
+                } else if (PAIR) {
                   // M = 256 across the pair: each CTA's tensor core reads its own A rows and both CTAs' weight halves
 #pragma unroll
                   for (int k = 0; k < kBK / 16; ++k) {     // 4 K steps of 32 bytes per 128-byte block (16 halves or 8 TF32 words)
@@ -647,7 +673,8 @@ static int launch(const CUtensorMap* maps, Params& p, cudaStream_t stream, int m
   using C = Cfg<BN>;
   const int a_stage = 2 * p.a_plane;
   // ring depths within kRingBudget: both rings hide the same TMA latency, so deepen A (up to 4) while B keeps >= 3 stages
-  const int budget = kRingBudget, b_stage = PAIR ? C::kBTile : 2 * C::kBTile;      // a pair's CTA stages half of the weight rows
+  // a pair's CTA stages half of the weight rows; narrow pair tiles: a whole plane + half of w_hi (see the kernel)
+  const int budget = kRingBudget, b_stage = (PAIR && BN <= 64) ? C::kBTile * 3 / 2 : PAIR ? C::kBTile : 2 * C::kBTile;
   const int sa_cap = max_sa > 0 && max_sa < kMaxSA ? max_sa : kMaxSA;      // debug knobs (rnc_conv_umma_desc.flags bits 8-15)
   p.SA = 2;
   while (p.SA < sa_cap && budget - (p.SA + 1) * a_stage >= 3 * b_stage) ++p.SA;

@@ -1,3 +1,4 @@
+export RNC_GRAPH=0
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02_infer_n8.json 2> gpurun_out/r02_infer_n8.err
-tail -c 600 gpurun_out/r02_infer_n8.err; cut -c1-400 gpurun_out/r02_infer_n8.json
+(timeout 900 python -m pytest tests/test_gpu_umma.py tests/test_gpu_encoder.py tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -5; python tools/l1_probe.py | head -4; python tools/iter_kernels.py | grep "128->64\|256->18\|sum"; python tools/step_breakdown.py | grep "step\|enc\|update") > gpurun_out/fused64.log 2>&1
+cat gpurun_out/fused64.log
