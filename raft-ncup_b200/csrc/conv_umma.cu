@@ -160,7 +160,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
       // pair: both CTAs' loads complete on the LEADER's full barriers (it alone waits for operands); each CTA recycles its
       // own stages when the leader's MMA completion reaches its own empty barriers
       const uint32_t a_full_l = PAIR ? mapa_u32(smem_u32(a_full), 0) : 0u, b_full_l = PAIR ? mapa_u32(smem_u32(b_full), 0) : 0u;
-      int a_it = 0, b_it = 0;
+      // ring positions as (slot, parity) counters: a runtime modulo per stage costs ~100 cycles of dependent integer code in
+      // these single-thread loops, which the 32-cycle MMAs of narrow tiles do not hide
+      int sa_n = 0, pa_n = 0, sb_n = 0, pb_n = 0, b_it = 0;
       for (int item = item0; item < items; item += item_step) {
         const int ptile = item / p.ntn, n0 = (item - ptile * p.ntn) * BN;
         const int tile = PAIR ? ptile * 2 + static_cast<int>(rank) : ptile;     // a ghost tile (odd count) loads zero-filled boxes
@@ -172,8 +174,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
           else if (p.mode == MODE_ROWHALO) { cx = x0 - p.pw; cy = y0 + g - p.ph; }
           else { cx = x0; cy = y0 - p.ph; }
           for (int cb = 0; cb < p.nblk; ++cb) {
-            const int sa = a_it % p.SA, pa = (a_it / p.SA) & 1;
-            ++a_it;
+            const int sa = sa_n, pa = pa_n;
+            if (++sa_n == p.SA) { sa_n = 0; pa_n ^= 1; }
             mbar_wait(&a_empty[sa], pa ^ 1);
             const bool seg0 = cb < p.nblk0;
             const int c = (seg0 ? cb : cb - p.nblk0) * p.bk;
@@ -191,7 +193,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
             __syncwarp();
             for (int t = 0; t < T; ++t) {
               const int tap = p.mode == MODE_TAP ? g : p.mode == MODE_ROWHALO ? g * p.kw + t : t;
-              const int sb = b_it % p.SB, pb = (b_it / p.SB) & 1;
+              const int sb = sb_n, pb = pb_n;
+              if (++sb_n == p.SB) { sb_n = 0; pb_n ^= 1; }
               ++b_it;
               if (p.resident_b && item != item0) continue;     // weights already resident
               mbar_wait(&b_empty[sb], pb ^ 1);
@@ -233,7 +236,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
       const bool tf32 = p.tf32 != 0;
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
       const int shift_rows = p.mode == MODE_ROWHALO ? 1 : p.mode == MODE_COLHALO ? p.TW : 0;
-      int a_it = 0, b_it = 0, t_it = 0;
+      int sa_n = 0, pa_n = 0, sb_n = 0, pb_n = 0, t_it = 0;
       for (int item = item0; item < items; item += item_step, ++t_it) {
         const int buf = t_it % C::kBufs, use = t_it / C::kBufs;
         mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
@@ -242,12 +245,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
         uint32_t acc = 0;
         for (int g = 0; g < G; ++g)
           for (int cb = 0; cb < p.nblk; ++cb) {
-            const int sa = a_it % p.SA, pa = (a_it / p.SA) & 1;
-            ++a_it;
+            const int sa = sa_n, pa = pa_n;
+            if (++sa_n == p.SA) { sa_n = 0; pa_n ^= 1; }
             mbar_wait(&a_full[sa], pa);
             for (int t = 0; t < T; ++t) {
-              const int sb = b_it % p.SB, pb = (b_it / p.SB) & 1;
-              ++b_it;
+              const int sb = sb_n, pb = pb_n;
+              if (++sb_n == p.SB) { sb_n = 0; pb_n ^= 1; }
               mbar_wait(&b_full[sb], p.resident_b ? 0 : pb);
               tcgen05_fence_after();
               const uint32_t ar = a_base + sa * a_stage + t * shift_rows * 128;
