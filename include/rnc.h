@@ -122,7 +122,7 @@ typedef enum {
 
 /* rnc_conv_umma_desc.flags */
 #define RNC_CONV_NO_HALO 1          /* force one A tile per filter tap (disable the row/column halo sharing) */
-#define RNC_CONV_BASE_OFFSET 2      /* debug: set the descriptor base_offset for row-shifted taps (wrong on B200) */
+#define RNC_CONV_BASE_OFFSET 2      /* reserved (round-1 debug switch for the descriptor base_offset; ignored)  */
 #define RNC_CONV_AUX_BLOCKED 16     /* aux0 (z gate) and add are tile-blocked: element (tile, channel c, row r) at ((tile*ld + c)*128 + r) */
 #define RNC_CONV_OUT_BLOCKED 32     /* RNC_EPI_LINEAR: out_f32 in the same tile-blocked layout (produces an `add` operand)          */
 #define RNC_CONV_NO_PAIR 8          /* never use the CTA-pair (cta_group::2) form for this call */

@@ -42,7 +42,6 @@ struct Params {
   int bk;                             // channels per K block: 64 (fp16 hi/lo operands) or 32 (TF32 hi/lo operands)
   int tf32;                           // operands are fp32 planes consumed as TF32 (kind::tf32): training-path layers
   int a_plane, SA, SB;                // bytes per A half-plane stage (rows*128, 1024-aligned), ring depths
-  int use_base_offset;
   int resident_b;                     // the layer's whole weight matrix fits the B ring: loaded once per CTA, never released
   int probe_nob;                      // developer probe (RNC_CONV_PROBE_NOB=1): skip the weight loads after the first ring fill
   int cout, epilogue;
@@ -57,11 +56,6 @@ struct Params {
   int aux_blocked, out_blocked;       // aux0 + add / out_f32 in the tile-blocked layout [tile][channel][128 px] (coalesced for thread = pixel)
   double* stats;                      // [B][cout][2]: per-(image, channel) sum / sum of squares of the outputs, accumulated
 };
-
-// K-major SW128 descriptor with a row shift inside the 8-row swizzle atom (base_offset = (addr >> 7) & 7)
-__device__ __forceinline__ uint64_t smem_desc_sw128_shift(uint32_t saddr) {
-  return smem_desc_sw128(saddr) | (static_cast<uint64_t>((saddr >> 7) & 7u) << 49);
-}
 
 // exact hi/lo split of 8 floats into two 16-byte vectors of halves
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
@@ -234,8 +228,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
       const uint32_t idesc = (1u << 4) | fmt | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>((PAIR ? 2 * kBM : kBM) >> 4) << 24);
       const uint32_t idesc2 = (1u << 4) | fmt | (static_cast<uint32_t>((2 * BN <= 256 ? 2 * BN : BN) >> 3) << 17) | (static_cast<uint32_t>(kBM >> 4) << 24);
       const bool tf32 = p.tf32 != 0;
-      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-      const int shift_rows = p.mode == MODE_ROWHALO ? 1 : p.mode == MODE_COLHALO ? p.TW : 0;
+      // Operand descriptors differ only in their address field (bits [0,14) = byte address >> 4, stages and tap shifts are
+      // multiples of 16 bytes and shared memory ends below 256 KB): stage 0's descriptor + one multiply-add per use, instead
+      // of rebuilding the 64-bit word from the address in this single-thread loop.  A descriptor whose start is shifted by kx
+      // rows needs no base_offset: with 1024-byte-aligned stages the swizzle is a function of the absolute address.
+      const uint64_t a_desc0 = smem_desc_sw128(smem_u32(sA)), b_desc0 = smem_desc_sw128(smem_u32(sB));
+      const uint32_t a_step = static_cast<uint32_t>(a_stage) >> 4, a_lo = static_cast<uint32_t>(p.a_plane) >> 4;
+      const uint32_t t_step = static_cast<uint32_t>(p.mode == MODE_ROWHALO ? 1 : p.mode == MODE_COLHALO ? p.TW : 0) * 8u;   // tap shift: rows * 128 B >> 4
       int sa_n = 0, pa_n = 0, sb_n = 0, pb_n = 0, t_it = 0;
       for (int item = item0; item < items; item += item_step, ++t_it) {
         const int buf = t_it % C::kBufs, use = t_it / C::kBufs;
@@ -253,14 +252,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mA0h, const __grid_constant
               if (++sb_n == p.SB) { sb_n = 0; pb_n ^= 1; }
               mbar_wait(&b_full[sb], p.resident_b ? 0 : pb);
               tcgen05_fence_after();
-              const uint32_t ar = a_base + sa * a_stage + t * shift_rows * 128;
-              const uint64_t ah = p.use_base_offset ? smem_desc_sw128_shift(ar) : smem_desc_sw128(ar);
-              const uint64_t al = p.use_base_offset ? smem_desc_sw128_shift(ar + p.a_plane) : smem_desc_sw128(ar + p.a_plane);
-              const uint32_t br = b_base + sb * kBStageBytes;
-              const uint64_t bh = smem_desc_sw128(br), bl = smem_desc_sw128(br + kBHalf);
+              const uint64_t ah = a_desc0 + (sa * a_step + t * t_step), al = ah + a_lo;
+              const uint64_t bh = b_desc0 + sb * (kBStageBytes >> 4), bl = bh + (kBHalf >> 4);
               if (elect_one()) {
                 if (kFusedPair) {
-                  const uint64_t bx = smem_desc_sw128(br), by = smem_desc_sw128(br + C::kBTile);
+                  const uint64_t bx = bh, by = bh + (C::kBTile >> 4);
                   const uint32_t idesc_x = (1u << 4) | fmt | (static_cast<uint32_t>((2 * BN) >> 3) << 17) | (static_cast<uint32_t>((2 * kBM) >> 4) << 24);
 #pragma unroll
                   for (int k = 0; k < kBK / 16; ++k) {
@@ -882,9 +878,6 @@ extern "C" int rnc_conv2d_umma_fwd(const rnc_conv_umma_desc* desc, void* stream)
   }
   if (box_w * box_h > 256 - 8 && mode == MODE_COLHALO) return RNC_ERR_UNSUPPORTED;   // kh <= 9
   p.mode = mode; p.TW = TW; p.TH = TH;
-  // Measured on B200: with 1024-byte-aligned stages the 128B swizzle is a function of the absolute shared-memory address,
-  // so a descriptor whose start is shifted by kx rows (kx*128 B) needs NO base_offset; setting it breaks the result.
-  p.use_base_offset = (d.flags & RNC_CONV_BASE_OFFSET) ? 1 : 0;
   {
     static const char* env = getenv("RNC_CONV_PROBE_NOB");
     p.probe_nob = env != nullptr && env[0] == '1';
