@@ -1,4 +1,4 @@
-export RNC_GRAPH=0
 mkdir -p gpurun_out
-(timeout 900 python -m pytest tests/test_gpu_umma.py tests/test_gpu_encoder.py tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -3; python tools/l1_probe.py 2>/dev/null | head -3; python tools/iter_kernels.py) > gpurun_out/desc.log 2>&1
-cat gpurun_out/desc.log
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -4 > gpurun_out/final_tests.log
+cat gpurun_out/final_tests.log
+bash tools/profile_r02.sh
