@@ -8,7 +8,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "raft-ncup_b200"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
-from conftest import build_model  # noqa: E402
+from rnc.synth import build_model  # noqa: E402
 
 dev = "cuda:0"
 m = build_model("raft_nc_dbl").to(dev)

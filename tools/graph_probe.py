@@ -3,7 +3,7 @@ import os, sys, time, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "raft-ncup_b200"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
-from conftest import build_model
+from rnc.synth import build_model
 sys.argv = [sys.argv[0]]
 import bench
 dev = "cuda:0"

@@ -4,7 +4,7 @@ for f in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
     if os.path.exists(f): print(f, open(f).read().strip())
 os.system("grep -m1 'model name' /proc/cpuinfo; free -g | head -2")
 sys.path.insert(0, '.'); sys.path.insert(0, 'raft-ncup_b200'); sys.path.insert(0, 'tests')
-from conftest import build_model, frames
+from rnc.synth import build_model, frames
 from oracle import raft_oracle as orc
 sd = {k: v.detach() for k, v in build_model("raft_nc_dbl").state_dict().items()}
 im1, im2 = frames(1, 128, 256)

@@ -4,7 +4,7 @@ import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "raft-ncup_b200"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
-from conftest import build_model, frames
+from rnc.synth import build_model, frames
 
 B, H, W, iters = int(os.environ.get("B", 8)), 440, 1024, 32
 dev = "cuda:0"
