@@ -109,6 +109,19 @@ def test_umma_conv_desc_layout_matches_header():
     assert ctypes.sizeof(UmmaConvDesc) == (expect + 7) // 8 * 8
 
 
+def test_flag_and_epilogue_constants_match_header():
+    """rnc.native mirrors the header's enums and flag bits by value (ctypes passes plain ints)."""
+    from rnc import native
+    hdr = open(os.path.join(ROOT, "include", "rnc.h")).read()
+    flags = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+RNC_CONV_([A-Z0-9_]+)\s+(\d+)", hdr)}
+    for name in ("NO_HALO", "SPLIT_N", "NO_PAIR", "AUX_BLOCKED", "OUT_BLOCKED", "TF32", "WINDOW"):
+        assert getattr(native, "CONV_" + name) == flags[name], name
+    epis = {m.group(1): int(m.group(2)) for m in re.finditer(r"RNC_EPI_([A-Z_]+)\s*=\s*(\d+)", hdr)}
+    for name in ("LINEAR", "RELU", "SIGMOID", "GRU_ZR", "GRU_Q", "RELU_FLOW", "RELU_ADD_RELU", "TANH_RELU", "FLOW_DELTA"):
+        assert getattr(native, "EPI_" + name) == epis[name], name
+    assert int(re.search(r"signature change \(now (\d+)\)", hdr).group(1)) == native.ABI_VERSION
+
+
 def test_cpu_tensors_fail_loudly_no_fallback():
     from rnc.native import RncUnavailable
     m = build_model("raft_nc_dbl")
